@@ -1,0 +1,91 @@
+"""ctypes binding of libfrs_b200.so (C ABI declared in include/frs_b200.h).
+
+The library is the only compute path: if it is missing this module raises — there is no CPU or
+PyTorch fallback (tests/ and bench.py rely on that to prove the CUDA path is the one that runs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfrs_b200.so")
+
+FRS_OK = 0
+FRS_DTYPE_F32 = 0
+FRS_DTYPE_BF16 = 1
+FRS_DIM = 384
+FRS_MAX_BATCH = 32
+FRS_MAX_K = 16
+CODE_TICKER_MASK = 0x00FFFFFF
+CODE_DOCTYPE_SHIFT = 24
+CODE_DOCTYPE_MASK = 0x7F000000
+CODE_TOMBSTONE = 0x80000000
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+
+# name -> (restype, argtypes); mirrors include/frs_b200.h one to one
+PROTOTYPES = {
+    "frs_version": (_int, []),
+    "frs_last_error": (C.c_char_p, []),
+    "frs_device_count": (_int, []),
+    "frs_index_create": (_int, [_int, _int, _i64, _int, C.POINTER(_vp)]),
+    "frs_index_destroy": (_int, [_vp]),
+    "frs_index_size": (_i64, [_vp]),
+    "frs_index_capacity": (_i64, [_vp]),
+    "frs_index_dtype": (_int, [_vp]),
+    "frs_index_set_base": (_int, [_vp, _i64]),
+    "frs_index_set_scan_grid": (_int, [_vp, _int]),
+    "frs_index_add": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "frs_index_add_host": (_int, [_vp, _vp, _vp, _i64]),
+    "frs_index_set_rows": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "frs_index_set_codes": (_int, [_vp, _i64, _vp, _i64, _vp]),
+    "frs_index_read_rows": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "frs_index_read_rows_host": (_int, [_vp, _i64, _i64, _vp]),
+    "frs_index_rows_ptr": (_vp, [_vp]),
+    "frs_index_codes_ptr": (_vp, [_vp]),
+    "frs_index_set_size": (_int, [_vp, _i64]),
+    "frs_index_search": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
+    "frs_index_search_host": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "frs_index_search_local": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
+    "frs_merge_shards": (_int, [_int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
+    "frs_index_last_queries": (_int, [_vp, _vp, _vp]),
+    "frs_index_debug_scores": (_int, [_vp, _vp, _int, _vp, _vp]),
+    "frs_index_last_stats": (_int, [_vp, C.POINTER(_i64)]),
+}
+
+_lib = None
+
+
+class FrsError(RuntimeError):
+    """Non-zero status from the C ABI (message from frs_last_error())."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"frs_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """Load libfrs_b200.so once.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(LIB_PATH)}` "
+                "or `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for the retrieval path."
+            )
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != FRS_OK:
+        raise FrsError(rc, lib().frs_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,79 @@
+// scan.cuh — launch interface of the exact cosine top-k scan (kernels in scan.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace frs {
+
+constexpr int kDim = 384;       // VectorParams(size=384)            reference ingest.py:89-95
+constexpr int kNQ = 32;         // queries per pass == MMA N         reference main2.py:51
+constexpr int kTileM = 128;     // corpus rows per tile == MMA M
+constexpr int kSlabBytes = kTileM * 128;  // 128 rows x 128 B: one SWIZZLE_128B K-slab (16 KiB)
+constexpr int kListCap = 64;    // per-query candidate list capacity inside a CTA
+constexpr int kKeep = 32;       // most entries a list keeps after a compaction
+constexpr int kMaxK = 16;       // largest `limit` supported              reference main.py:215
+constexpr int kAccStages = 8;   // TMEM accumulator ring (8 x 32 columns)
+constexpr int kTmemCols = kAccStages * kNQ;
+constexpr int kScanThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kMergeThreads = 256;
+
+// bound on |tensor-core pre-filter score - fp64 score| for unit-norm rows and queries
+constexpr float kEpsBF16 = 3.0e-5f;  // exact products, fp32 accumulation of 384 terms
+constexpr float kEpsTF32 = 2.0e-3f;  // 2^-9 operand truncation (Cauchy-Schwarz) + accumulation
+
+enum StatSlot { kStatAppended = 0, kStatCompactions = 1, kStatResolutions = 2, kStatRescored = 3, kStatSlots = 8 };
+
+struct ScanParams {
+  const void* rows;        // [capacity, 384] storage dtype
+  const uint32_t* codes;   // [capacity] payload codes
+  uint32_t n;              // rows in use
+  uint32_t num_tiles;      // ceil(n / 128)
+  const float* qrec;       // [32, 384] prepared queries widened to fp32 (exact rescoring operand)
+  const uint32_t* qcode;   // [32]
+  const uint32_t* qmask;   // [32]
+  int nq;                  // live queries (<= 32)
+  int k;                   // top-k (<= kMaxK)
+  float eps;               // pre-filter error bound
+  uint64_t* part_keys;     // [grid, 32, kKeep] surviving (approx score, row) keys per CTA
+  uint32_t* part_cnt;      // [grid, 32]
+  float* dbg_scores;       // DUMP mode only: [32, n]
+  unsigned long long* stats;  // [kStatSlots]
+};
+
+struct MergeParams {
+  const uint64_t* part_keys;
+  const uint32_t* part_cnt;
+  int nparts;
+  const void* rows;
+  const float* qrec;
+  int nq;
+  int k;
+  float eps;
+  int64_t base;        // global id of local row 0
+  double* out_s64;     // [nq, k] or null
+  float* out_s32;      // [nq, k] or null
+  int64_t* out_ids;    // [nq, k]
+  unsigned long long* stats;
+};
+
+size_t scan_smem_bytes(bool f32);
+size_t merge_smem_bytes(int nparts);
+
+// all launchers return the cudaError_t of configuration + launch
+cudaError_t launch_scan(bool f32, bool dump, int grid, const CUtensorMap& tmap_rows,
+                        const CUtensorMap& tmap_q, const ScanParams& p, cudaStream_t st);
+cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st);
+cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
+                                float* out_s32, int64_t* out_ids, cudaStream_t st);
+// queries [nq,384] fp32 -> qop (MMA operand, bf16 or tf32-rounded fp32, zero padded to 32 rows),
+// qrec (fp32 record copy), qcode/qmask copies padded to 32
+cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, const uint32_t* mask,
+                                int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
+                                unsigned long long* stats, cudaStream_t st);
+// rows [n,384] fp32 -> L2-normalised storage rows (+ codes) at dst row offset
+cudaError_t launch_store_rows(bool f32, const float* vecs, const uint32_t* codes, int64_t n,
+                              void* rows_dst, uint32_t* codes_dst, cudaStream_t st);
+cudaError_t launch_read_rows(bool f32, const void* rows_src, int64_t n, float* out, cudaStream_t st);
+
+}  // namespace frs

@@ -1,0 +1,180 @@
+"""VectorIndex — thin Python handle on one GPU shard of the chunk store (C ABI: include/frs_b200.h).
+
+PyTorch is used for device memory and streams only; every kernel launched here is from
+libfrs_b200.so.  Replaces the Qdrant collection of the reference (create_collection
+ingest.py:86-96, upsert ingest.py:171-175, query_points main.py:232-237).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FRS_DIM, FRS_DTYPE_BF16, FRS_DTYPE_F32, FRS_MAX_BATCH, FRS_MAX_K, check
+
+_DTYPES = {"bf16": FRS_DTYPE_BF16, "f32": FRS_DTYPE_F32, "fp32": FRS_DTYPE_F32}
+
+
+def _ptr(t) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class VectorIndex:
+    """One shard: `capacity` rows x 384, stored L2-normalised in bf16 or fp32 on one GPU."""
+
+    def __init__(self, capacity: int, dtype: str = "bf16", device: int = 0, base: int = 0):
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        self._lib = _lib.lib()
+        self.dtype = "f32" if _DTYPES[dtype] == FRS_DTYPE_F32 else "bf16"
+        self.device = torch.device("cuda", device)
+        self.capacity = int(capacity)
+        self.base = int(base)
+        h = C.c_void_p()
+        check(self._lib.frs_index_create(device, FRS_DIM, self.capacity, _DTYPES[dtype], C.byref(h)))
+        self._h = h
+        check(self._lib.frs_index_set_base(self._h, self.base))
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.frs_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self._lib.frs_index_size(self._h))
+
+    # -- write path -----------------------------------------------------------------------------
+    def add(self, vecs, codes=None) -> None:
+        """Append rows.  vecs [n,384] float32 (torch cuda tensor or numpy), codes [n] uint32/int32."""
+        if isinstance(vecs, torch.Tensor):
+            v = vecs.to(device=self.device, dtype=torch.float32).contiguous()
+            if v.dim() != 2 or v.shape[1] != FRS_DIM:
+                raise ValueError("vecs must be [n, 384]")
+            c = None
+            if codes is not None:
+                c = torch.as_tensor(codes).to(device=self.device).contiguous()
+                if c.dtype not in (torch.int32, torch.uint32):
+                    c = c.to(torch.int64).to(torch.int32)
+                if c.numel() != v.shape[0]:
+                    raise ValueError("codes must be [n]")
+            check(self._lib.frs_index_add(self._h, _ptr(v), _ptr(c), v.shape[0], _stream_ptr(self.device)))
+            # keep v/c alive until the kernel has consumed them
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            v = np.ascontiguousarray(vecs, dtype=np.float32)
+            if v.ndim != 2 or v.shape[1] != FRS_DIM:
+                raise ValueError("vecs must be [n, 384]")
+            c = None if codes is None else np.ascontiguousarray(codes).astype(np.uint32)
+            check(self._lib.frs_index_add_host(self._h, _ptr(v), _ptr(c), v.shape[0]))
+
+    def set_rows(self, row0: int, vecs: torch.Tensor, codes: torch.Tensor | None = None) -> None:
+        v = vecs.to(device=self.device, dtype=torch.float32).contiguous()
+        c = None if codes is None else codes.to(device=self.device, dtype=torch.int32).contiguous()
+        check(self._lib.frs_index_set_rows(self._h, int(row0), _ptr(v), _ptr(c), v.shape[0], _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def set_codes(self, row0: int, codes: torch.Tensor) -> None:
+        c = codes.to(device=self.device, dtype=torch.int32).contiguous()
+        check(self._lib.frs_index_set_codes(self._h, int(row0), _ptr(c), c.numel(), _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def read_rows(self, row0: int = 0, n: int | None = None) -> torch.Tensor:
+        n = len(self) - row0 if n is None else n
+        out = torch.empty((n, FRS_DIM), dtype=torch.float32, device=self.device)
+        check(self._lib.frs_index_read_rows(self._h, int(row0), int(n), _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def set_scan_grid(self, grid: int) -> None:
+        check(self._lib.frs_index_set_scan_grid(self._h, int(grid)))
+
+    # -- search ---------------------------------------------------------------------------------
+    @staticmethod
+    def _check_batch(nq: int, k: int) -> None:
+        if not 1 <= nq <= FRS_MAX_BATCH:
+            raise ValueError(f"1..{FRS_MAX_BATCH} queries per call (got {nq})")
+        if not 1 <= k <= FRS_MAX_K:
+            raise ValueError(f"k must be in 1..{FRS_MAX_K} (got {k})")
+
+    def search(self, queries, q_code, q_mask, k: int = 15):
+        """Exact cosine top-k.  Device tensors in -> device tensors out (async on the current
+        stream); numpy in -> numpy out through the host entry point (copies inside the call).
+        Returns (ids int64 [nq,k], scores float32 [nq,k])."""
+        if isinstance(queries, torch.Tensor):
+            q = queries.to(device=self.device, dtype=torch.float32).contiguous()
+            nq = q.shape[0]
+            self._check_batch(nq, k)
+            qc = torch.as_tensor(q_code).to(device=self.device, dtype=torch.int32).contiguous()
+            qm = torch.as_tensor(q_mask).to(device=self.device, dtype=torch.int32).contiguous()
+            scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            check(self._lib.frs_index_search(self._h, _ptr(q), _ptr(qc), _ptr(qm), nq, k, _ptr(scores), _ptr(ids),
+                                             _stream_ptr(self.device)))
+            # q/qc/qm are consumed by kernels already enqueued on this stream; record them so the
+            # caching allocator does not hand the memory to another stream early
+            for t in (q, qc, qm):
+                t.record_stream(torch.cuda.current_stream(self.device))
+            return ids, scores
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        self._check_batch(nq, k)
+        qc = np.ascontiguousarray(np.asarray(q_code, dtype=np.int64).astype(np.uint32))
+        qm = np.ascontiguousarray(np.asarray(q_mask, dtype=np.int64).astype(np.uint32))
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        check(self._lib.frs_index_search_host(self._h, _ptr(q), _ptr(qc), _ptr(qm), nq, k, _ptr(scores), _ptr(ids)))
+        return ids, scores
+
+    def search_local(self, q: torch.Tensor, qc: torch.Tensor, qm: torch.Tensor, k: int,
+                     out_scores64: torch.Tensor, out_ids: torch.Tensor) -> None:
+        """Shard-local pass of a sharded search: exact local top-k as (float64, int64 global id)."""
+        self._check_batch(q.shape[0], k)
+        check(self._lib.frs_index_search_local(self._h, _ptr(q), _ptr(qc), _ptr(qm), q.shape[0], k,
+                                               _ptr(out_scores64), _ptr(out_ids), _stream_ptr(self.device)))
+
+    def last_queries(self) -> torch.Tensor:
+        out = torch.empty((FRS_MAX_BATCH, FRS_DIM), dtype=torch.float32, device=self.device)
+        check(self._lib.frs_index_last_queries(self._h, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def debug_scores(self, queries: torch.Tensor) -> torch.Tensor:
+        """Raw tensor-core pre-filter scores [32, n] (diagnostics)."""
+        q = queries.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.zeros((FRS_MAX_BATCH, len(self)), dtype=torch.float32, device=self.device)
+        check(self._lib.frs_index_debug_scores(self._h, _ptr(q), q.shape[0], _ptr(out), _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def last_stats(self) -> dict:
+        buf = (C.c_int64 * 6)()
+        check(self._lib.frs_index_last_stats(self._h, buf))
+        keys = ("appended", "compactions", "resolutions", "rescored", "grid", "launches")
+        return dict(zip(keys, [int(x) for x in buf]))
+
+
+def merge_shards(scores64: torch.Tensor, ids: torch.Tensor, k: int):
+    """[n_shards, nq, k] exact candidates -> ([nq,k] ids, [nq,k] float32 scores), on device."""
+    n_shards, nq, kk = scores64.shape
+    assert kk == k and ids.shape == scores64.shape
+    dev = scores64.device
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    check(_lib.lib().frs_merge_shards(dev.index or 0, _ptr(scores64.contiguous()), _ptr(ids.contiguous()), n_shards, nq, k,
+                                      _ptr(out_s), _ptr(out_i), _stream_ptr(dev)))
+    return out_i, out_s

@@ -1,0 +1,167 @@
+/*
+ * frs_b200.h — C ABI of the B200-native retrieval hot path.
+ *
+ * This is the drop-in boundary for the three calls the reference makes into
+ * third-party libraries on its hot path (all citations are into the reference
+ * repository, pythonmailer/financial-rag-system):
+ *
+ *   SentenceTransformer.encode(texts)     main.py:148, main.py:213, main2.py:171
+ *   QdrantClient.query_points(...)        main.py:232-237, main2.py:163
+ *   QdrantClient.upsert(points=...)       ingest.py:171-175
+ *   CrossEncoder.predict(pairs)           main.py:245, main2.py:166
+ *
+ * The reference has no FFI of its own (it is pure Python); this header is what
+ * a ctypes binding in main.py/ingest.py binds instead of the three packages.
+ * INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - every entry point returns 0 (FRS_OK) or a negative FRS_E_* code; the
+ *     message is available from frs_last_error() (thread local).  Nothing
+ *     throws across the boundary.
+ *   - "dev" pointers are device pointers owned by the caller, "host" pointers
+ *     are ordinary host memory.  Handles are owned by the library.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *     stream).  Device-pointer entry points are asynchronous on that stream.
+ *   - strings never cross the boundary: ticker / document_type are integer
+ *     codes (see FRS_CODE_* below), ids are row numbers; the uuid / payload
+ *     tables live in the Python shim.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with FRS_E_CUDA.
+ */
+#ifndef FRS_B200_H_
+#define FRS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRS_VERSION 100 /* 0.1.0 */
+
+#define FRS_OK 0
+#define FRS_E_INVALID (-1) /* bad argument                               */
+#define FRS_E_CUDA (-2)    /* CUDA runtime / driver error                */
+#define FRS_E_CAPACITY (-3) /* index full                                */
+#define FRS_E_STATE (-4)   /* call not valid in this state               */
+
+#define FRS_DIM 384      /* VectorParams(size=384)  ingest.py:89-95        */
+#define FRS_MAX_BATCH 32 /* MAX_BATCH_SIZE          main2.py:51            */
+#define FRS_MAX_K 16     /* limit=15                main.py:215            */
+
+/* storage / arithmetic modes of the chunk store */
+#define FRS_DTYPE_F32 0  /* rows kept in fp32, TF32 tensor-core pre-filter + fp64 rescoring */
+#define FRS_DTYPE_BF16 1 /* rows kept in bf16, bf16 tensor-core pre-filter + fp64 rescoring */
+
+/*
+ * Per-row payload code (uint32): the keyword payloads the reference filters on
+ * (`ticker`, `document_type`; main.py:218-230) folded into one word.
+ *   bits  0..23  ticker id        (dictionary kept by the Python shim)
+ *   bits 24..30  document_type id
+ *   bit  31      tombstone (row deleted / superseded by an upsert)
+ * A query carries (code, mask): a row matches iff ((row_code ^ code) & mask) == 0.
+ * The shim always sets bit 31 in `mask` so tombstones never match.
+ */
+#define FRS_CODE_TICKER_MASK 0x00FFFFFFu
+#define FRS_CODE_DOCTYPE_SHIFT 24
+#define FRS_CODE_DOCTYPE_MASK 0x7F000000u
+#define FRS_CODE_TOMBSTONE 0x80000000u
+
+typedef struct frs_index frs_index;
+typedef struct frs_encoder frs_encoder;
+
+/* ---- library ---------------------------------------------------------- */
+int frs_version(void);
+const char* frs_last_error(void);
+/* number of visible CUDA devices, or a negative error code */
+int frs_device_count(void);
+
+/* ---- chunk store: replaces the Qdrant collection ----------------------
+ * create_collection(VectorParams(size=384, distance=COSINE))  ingest.py:86-96, database.py:111-143 */
+int frs_index_create(int device, int dim, int64_t capacity, int dtype, frs_index** out);
+int frs_index_destroy(frs_index* idx);
+int64_t frs_index_size(const frs_index* idx);
+int64_t frs_index_capacity(const frs_index* idx);
+int frs_index_dtype(const frs_index* idx);
+/* first global row id of this shard (ids returned by search = base + local row) */
+int frs_index_set_base(frs_index* idx, int64_t base);
+/* number of CTAs of the scan kernel (0 = one per SM).  Results do not depend on it; exposed so
+ * the tests can prove that. */
+int frs_index_set_scan_grid(frs_index* idx, int grid);
+
+/* qdrant.upsert(points)  ingest.py:171-175: L2-normalise (cosine collection),
+ * convert to the storage dtype and append.  vecs: [n, 384] fp32, codes: [n]. */
+int frs_index_add(frs_index* idx, const float* dev_vecs, const uint32_t* dev_codes, int64_t n,
+                  void* stream);
+int frs_index_add_host(frs_index* idx, const float* host_vecs, const uint32_t* host_codes,
+                       int64_t n);
+/* overwrite rows [row0, row0+n) (idempotent upsert on an existing id) */
+int frs_index_set_rows(frs_index* idx, int64_t row0, const float* dev_vecs,
+                       const uint32_t* dev_codes, int64_t n, void* stream);
+/* overwrite payload codes only (tombstoning) */
+int frs_index_set_codes(frs_index* idx, int64_t row0, const uint32_t* dev_codes, int64_t n,
+                        void* stream);
+/* read stored rows back as fp32 (exact widening of the stored values) */
+int frs_index_read_rows(frs_index* idx, int64_t row0, int64_t n, float* dev_out, void* stream);
+int frs_index_read_rows_host(frs_index* idx, int64_t row0, int64_t n, float* host_out);
+/* raw device pointers (persistence / zero-copy fill); rows are [capacity, 384] of the dtype */
+void* frs_index_rows_ptr(frs_index* idx);
+uint32_t* frs_index_codes_ptr(frs_index* idx);
+/* declare that rows [0, n) were filled in place through frs_index_rows_ptr() */
+int frs_index_set_size(frs_index* idx, int64_t n);
+
+/* qdrant.query_points(query=vec, limit=k, query_filter=Filter(must=[...]))
+ * main.py:215-239, main2.py:160-163 — exact cosine top-k with payload filter.
+ *   queries      [nq, 384] fp32, nq <= FRS_MAX_BATCH (need not be normalised)
+ *   q_code/mask  [nq] per-query payload predicate (see FRS_CODE_*)
+ *   out_scores   [nq, k] fp32, descending; -inf where fewer than k rows match
+ *   out_ids      [nq, k] int64 global row ids (base + row); -1 where no row
+ * Ordering is (score desc, id asc) on the fp64 dot product of the stored rows
+ * with the prepared query — independent of grid size, GPU count and timing. */
+int frs_index_search(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
+                     const uint32_t* dev_q_mask, int nq, int k, float* dev_out_scores,
+                     int64_t* dev_out_ids, void* stream);
+int frs_index_search_host(frs_index* idx, const float* host_queries, const uint32_t* host_q_code,
+                          const uint32_t* host_q_mask, int nq, int k, float* host_out_scores,
+                          int64_t* host_out_ids);
+
+/* Sharded search (one shard per GPU / process): local pass that leaves the
+ * shard's exact top-k as (fp64 score, int64 global id) pairs for the exchange
+ * step, and the final merge over the gathered [n_shards, nq, k] candidates. */
+int frs_index_search_local(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
+                           const uint32_t* dev_q_mask, int nq, int k, double* dev_out_scores64,
+                           int64_t* dev_out_ids, void* stream);
+int frs_merge_shards(int device, const double* dev_scores64, const int64_t* dev_ids, int n_shards,
+                     int nq, int k, float* dev_out_scores, int64_t* dev_out_ids, void* stream);
+
+/* the prepared (normalised, storage-dtype-rounded) queries of the last search,
+ * widened to fp32: what the scores are dot products with.  [FRS_MAX_BATCH, 384] */
+int frs_index_last_queries(frs_index* idx, float* dev_out, void* stream);
+/* diagnostics: raw tensor-core pre-filter scores of every row, [nq_pad=32, n] fp32
+ * (row-major by query).  Test / profiling aid, not a product path. */
+int frs_index_debug_scores(frs_index* idx, const float* dev_queries, int nq, float* dev_out,
+                           void* stream);
+/* counters of the last search on this index: [0] candidates appended in the scan,
+ * [1] list compactions, [2] in-scan exact resolutions, [3] rows rescored in the merge,
+ * [4] scan grid size, [5] kernels launched by the last search call */
+int frs_index_last_stats(frs_index* idx, int64_t* host_out6);
+
+/* ---- encoders: replace SentenceTransformer.encode / CrossEncoder.predict -
+ * BertModel forward (transformers/models/bert/modeling_bert.py) for the two
+ * checkpoints of main.py:84,90.  Declared here; see encoder section of DESIGN.md. */
+typedef struct frs_bert_cfg {
+  int32_t vocab_size;    /* 30522 */
+  int32_t hidden;        /* 384   */
+  int32_t layers;        /* 12 (bge-small-en-v1.5) / 6 (ms-marco-MiniLM-L-6-v2) */
+  int32_t heads;         /* 12    */
+  int32_t intermediate;  /* 1536  */
+  int32_t max_pos;       /* 512   */
+  int32_t type_vocab;    /* 2     */
+  int32_t has_head;      /* 1 = pooler + 1-logit classifier (cross-encoder) */
+  float ln_eps;          /* 1e-12 */
+} frs_bert_cfg;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRS_B200_H_ */
