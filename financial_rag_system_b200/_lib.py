@@ -54,6 +54,9 @@ PROTOTYPES = {
     "frs_index_last_queries": (_int, [_vp, _vp, _vp]),
     "frs_index_debug_scores": (_int, [_vp, _vp, _int, _vp, _vp]),
     "frs_index_last_stats": (_int, [_vp, C.POINTER(_i64)]),
+    "frs_index_set_profiling": (_int, [_vp, _int]),
+    "frs_index_read_profile": (_int, [_vp, C.POINTER(C.c_double)]),
+    "frs_index_read_timeline": (_int, [_vp, _vp, _int]),
 }
 
 _lib = None

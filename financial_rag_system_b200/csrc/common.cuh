@@ -21,6 +21,11 @@ __device__ __forceinline__ uint32_t lane_id() {
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
   return l;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -90,11 +95,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > FRS_MBAR_SPIN_LIMIT) {
-      printf("frs: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x,
-             threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
+    if (++spins > FRS_MBAR_SPIN_LIMIT) __trap();  // no printf: it would give the kernel a stack frame
   }
 }
 
@@ -228,6 +229,32 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+// N columns (8 or 16) selected at compile time
+template <int N>
+__device__ __forceinline__ void tmem_ld_32xN(uint32_t taddr, uint32_t (&v)[N]) {
+  static_assert(N == 8 || N == 16 || N == 32, "unsupported TMEM load width");
+  if constexpr (N == 8) tmem_ld_32x8(taddr, v);
+  else if constexpr (N == 16) tmem_ld_32x16(taddr, v);
+  else tmem_ld_32x32(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

@@ -107,7 +107,15 @@ struct frs_index {
   uint64_t* part_keys = nullptr;
   uint32_t* part_cnt = nullptr;
   unsigned long long* stats = nullptr;
+  float* gmax = nullptr;
+  float* gsample = nullptr;
+  unsigned long long* timeline = nullptr;
   int max_parts = 0;
+  // profiling (off by default): CUDA events around each kernel of a search
+  static constexpr int kProfRing = 256;
+  int prof_mode = 0;          // 0 off, 1 events, 2 events + in-kernel timeline
+  int prof_calls = 0;         // searches recorded since the last read
+  cudaEvent_t* prof_ev = nullptr;  // [kProfRing][4]: before prep, after prep, after scan, after merge
   // staging for the *_host entry points
   float* d_q = nullptr;
   uint32_t* d_code = nullptr;
@@ -140,6 +148,13 @@ static void free_index(frs_index* ix) {
   cudaFree(ix->part_keys);
   cudaFree(ix->part_cnt);
   cudaFree(ix->stats);
+  cudaFree(ix->gmax);
+  cudaFree(ix->gsample);
+  cudaFree(ix->timeline);
+  if (ix->prof_ev) {
+    for (int i = 0; i < frs_index::kProfRing * 4; ++i) cudaEventDestroy(ix->prof_ev[i]);
+    delete[] ix->prof_ev;
+  }
   cudaFree(ix->d_q);
   cudaFree(ix->d_code);
   cudaFree(ix->d_mask);
@@ -175,7 +190,7 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
   ix->dtype = dtype;
   ix->capacity = capacity;
   ix->sm_count = prop.multiProcessorCount;
-  ix->max_parts = ix->sm_count;
+  ix->max_parts = ix->sm_count < kGmaxPad ? ix->sm_count : kGmaxPad;
   const bool f32 = ix->f32();
   // rows padded to a whole tile so a TMA box never straddles the allocation end
   const int64_t cap_pad = (capacity + kTileM - 1) / kTileM * kTileM;
@@ -196,10 +211,14 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
   IX_TRY(cudaMemset(ix->qrec, 0, (size_t)kNQ * kDim * 4));
   IX_TRY(cudaMalloc(&ix->qcode, kNQ * 4));
   IX_TRY(cudaMalloc(&ix->qmask, kNQ * 4));
-  IX_TRY(cudaMalloc(&ix->part_keys, (size_t)ix->max_parts * kNQ * kKeep * 8));
+  IX_TRY(cudaMalloc(&ix->part_keys, (size_t)ix->max_parts * kNQ * kListCap * 8));
   IX_TRY(cudaMalloc(&ix->part_cnt, (size_t)ix->max_parts * kNQ * 4));
   IX_TRY(cudaMalloc(&ix->stats, kStatSlots * 8));
   IX_TRY(cudaMemset(ix->stats, 0, kStatSlots * 8));
+  IX_TRY(cudaMalloc(&ix->gmax, (size_t)kNQ * kGmaxPad * 4));
+  IX_TRY(cudaMalloc(&ix->gsample, (size_t)kNQ * kSampleBlocks * 4));
+  IX_TRY(cudaMalloc(&ix->timeline, (size_t)kGmaxPad * 16 * 8));
+  IX_TRY(cudaMemset(ix->timeline, 0, (size_t)kGmaxPad * 16 * 8));
   IX_TRY(cudaMalloc(&ix->d_q, (size_t)kNQ * kDim * 4));
   IX_TRY(cudaMalloc(&ix->d_code, kNQ * 4));
   IX_TRY(cudaMalloc(&ix->d_mask, kNQ * 4));
@@ -379,8 +398,13 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
   // the workspace is shared by all calls on this index: order this call after the previous one
   CU_TRY(cudaStreamWaitEvent(st, ix->ws_free, 0));
   int launches = 0;
-  CU_TRY(launch_prep_queries(f32, q, code, mask, nq, ix->qop, ix->qrec, ix->qcode, ix->qmask, ix->stats, st));
+  cudaEvent_t* pev = nullptr;
+  if (ix->prof_mode && ix->prof_ev) pev = ix->prof_ev + (size_t)(ix->prof_calls % frs_index::kProfRing) * 4;
+  if (pev) CU_TRY(cudaEventRecord(pev[0], st));
+  CU_TRY(launch_prep_queries(f32, q, code, mask, nq, ix->qop, ix->qrec, ix->qcode, ix->qmask, ix->stats, ix->gmax,
+                             ix->gsample, ix->rows, ix->codes, (uint32_t)ix->size, st));
   launches++;
+  if (pev) CU_TRY(cudaEventRecord(pev[1], st));
   const uint32_t n = (uint32_t)ix->size;
   const uint32_t num_tiles = (n + kTileM - 1) / kTileM;
   const int grid = scan_grid(ix, num_tiles);
@@ -399,13 +423,19 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
     sp.part_keys = ix->part_keys;
     sp.part_cnt = ix->part_cnt;
     sp.dbg_scores = nullptr;
+    sp.gmax = ix->gmax;
+    sp.gsample = ix->gsample;
     sp.stats = ix->stats;
+    sp.timeline = ix->prof_mode == 2 ? ix->timeline : nullptr;
+    if (sp.timeline) CU_TRY(cudaMemsetAsync(ix->timeline, 0, (size_t)kGmaxPad * 16 * 8, st));
     CU_TRY(launch_scan(f32, false, grid, ix->tmap_rows, ix->tmap_q, sp, st));
     launches++;
   }
+  if (pev) CU_TRY(cudaEventRecord(pev[2], st));
   MergeParams mp{};
   mp.part_keys = ix->part_keys;
   mp.part_cnt = ix->part_cnt;
+  mp.gmax = ix->gmax;
   mp.nparts = grid;
   mp.rows = ix->rows;
   mp.qrec = ix->qrec;
@@ -419,6 +449,10 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
   mp.stats = ix->stats;
   CU_TRY(launch_merge(f32, mp, st));
   launches++;
+  if (pev) {
+    CU_TRY(cudaEventRecord(pev[3], st));
+    ix->prof_calls++;
+  }
   CU_TRY(cudaEventRecord(ix->ws_free, st));
   ix->last_grid = grid;
   ix->last_launches = launches;
@@ -499,7 +533,7 @@ extern "C" int frs_index_debug_scores(frs_index* idx, const float* dev_queries, 
   CU_TRY(cudaStreamWaitEvent(st, idx->ws_free, 0));
   CU_TRY(cudaMemsetAsync(idx->d_code, 0, kNQ * 4, st));
   CU_TRY(launch_prep_queries(f32, dev_queries, idx->d_code, idx->d_code, nq, idx->qop, idx->qrec, idx->qcode,
-                             idx->qmask, idx->stats, st));
+                             idx->qmask, idx->stats, idx->gmax, idx->gsample, idx->rows, idx->codes, (uint32_t)idx->size, st));
   const uint32_t n = (uint32_t)idx->size;
   const uint32_t num_tiles = (n + kTileM - 1) / kTileM;
   const int grid = scan_grid(idx, num_tiles);
@@ -516,6 +550,8 @@ extern "C" int frs_index_debug_scores(frs_index* idx, const float* dev_queries, 
     sp.k = 1;
     sp.eps = 0.f;
     sp.dbg_scores = dev_out;
+    sp.gmax = idx->gmax;
+    sp.gsample = idx->gsample;
     sp.stats = idx->stats;
     CU_TRY(launch_scan(f32, true, grid, idx->tmap_rows, idx->tmap_q, sp, st));
   }
@@ -534,5 +570,50 @@ extern "C" int frs_index_last_stats(frs_index* idx, int64_t* host_out6) {
   host_out6[3] = (int64_t)h[kStatRescored];
   host_out6[4] = idx->last_grid;
   host_out6[5] = idx->last_launches;
+  return FRS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// profiling
+// ---------------------------------------------------------------------------------------------
+extern "C" int frs_index_set_profiling(frs_index* idx, int mode) {
+  if (!idx || mode < 0 || mode > 2) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (mode && !idx->prof_ev) {
+    idx->prof_ev = new (std::nothrow) cudaEvent_t[frs_index::kProfRing * 4];
+    if (!idx->prof_ev) return set_err(FRS_E_INVALID, "out of host memory");
+    for (int i = 0; i < frs_index::kProfRing * 4; ++i) CU_TRY(cudaEventCreate(&idx->prof_ev[i]));
+  }
+  idx->prof_mode = mode;
+  idx->prof_calls = 0;
+  return FRS_OK;
+}
+
+extern "C" int frs_index_read_profile(frs_index* idx, double* host_out4) {
+  if (!idx || !host_out4) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  host_out4[0] = host_out4[1] = host_out4[2] = host_out4[3] = 0.0;
+  if (!idx->prof_ev || idx->prof_calls == 0) return FRS_OK;
+  const int n = idx->prof_calls < frs_index::kProfRing ? idx->prof_calls : frs_index::kProfRing;
+  for (int c = 0; c < n; ++c) {
+    cudaEvent_t* ev = idx->prof_ev + (size_t)((idx->prof_calls - 1 - c) % frs_index::kProfRing) * 4;
+    CU_TRY(cudaEventSynchronize(ev[3]));
+    for (int j = 0; j < 3; ++j) {
+      float ms = 0.f;
+      CU_TRY(cudaEventElapsedTime(&ms, ev[j], ev[j + 1]));
+      host_out4[1 + j] += ms;
+    }
+  }
+  host_out4[0] = n;
+  idx->prof_calls = 0;
+  return FRS_OK;
+}
+
+extern "C" int frs_index_read_timeline(frs_index* idx, uint64_t* host_out, int n_ctas) {
+  if (!idx || !host_out || n_ctas < 0 || n_ctas > kGmaxPad) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  CU_TRY(cudaMemcpy(host_out, idx->timeline, (size_t)n_ctas * 16 * 8, cudaMemcpyDeviceToHost));
   return FRS_OK;
 }

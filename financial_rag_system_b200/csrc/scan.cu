@@ -16,10 +16,15 @@
 // The result therefore equals the exact top-k of the fp64 scores whatever the grid size, the CTA
 // schedule or the GPU count — the property the parity tests check against oracle/search_oracle.py.
 //
-// Warp roles in scan_kernel (192 threads, one CTA per SM, persistent over tiles b, b+G, ...):
-//   warp 0   TMA producer: one 128x128B slab (SWIZZLE_128B) per mbarrier stage, ring of slabs
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (M=128 rows, N=32 queries, K=16|8)
-//   warp 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, payload filter, threshold, list insert
+// Warp roles in scan_kernel (352 threads, one CTA per SM, persistent over tiles b, b+G, ...):
+//   warp 0    TMA producer: one 128x128B slab (SWIZZLE_128B) per mbarrier stage, ring of slabs
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (M=128 rows, N=32 queries, K=16|8)
+//   warp 10   bound refresher: raises the pass thresholds from the cross-CTA table in the background
+//   warp 2-9  epilogue, 2 per SM sub-partition so their latencies overlap: warp w reads TMEM lane
+//             group w%4 (32 rows) x 16 query columns with tcgen05.ld, applies the payload filter
+//             and the per-query thresholds (fast path: 16 compares per row), and appends survivors
+//             to the CTA's per-query candidate lists (rare path).  No stack anywhere: the CTA
+//             leaves no L1, so local memory would cost an L2 round trip per access.
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -30,7 +35,7 @@ struct ScanCfg {
   static constexpr int kElemBytes = F32 ? 4 : 2;
   static constexpr int kSlabK = 128 / kElemBytes;       // elements per 128 B slab row (32 | 64)
   static constexpr int kSlabs = kDim / kSlabK;          // slabs per tile (12 | 6)
-  static constexpr int kRing = F32 ? 9 : 10;            // slabs in flight
+  static constexpr int kRing = F32 ? 8 : 10;            // slabs in flight
   static constexpr int kQSlabBytes = kNQ * 128;         // 4 KiB
   static constexpr int kQBytes = kSlabs * kQSlabBytes;  // 48 KiB | 24 KiB
   static constexpr int kMmasPerSlab = 4;                // each advances 32 B along K
@@ -43,14 +48,16 @@ struct ScanSmem {
   static constexpr size_t ring = 0;
   static constexpr size_t qop = ring + (size_t)C::kRing * kSlabBytes;
   static constexpr size_t keys = qop + C::kQBytes;                       // u64 [32][kListCap]
-  static constexpr size_t scratch = keys + (size_t)kNQ * kListCap * 8;   // f64 [4][kListCap]
-  static constexpr size_t cnt = scratch + 4 * kListCap * 8;              // u32 [32]
+  static constexpr size_t scratch = keys + (size_t)kNQ * kListCap * 8;   // f64 [kEpiWarps][kListCap]
+  static constexpr size_t cnt = scratch + (size_t)kEpiWarps * kListCap * 8;  // u32 [32]
   static constexpr size_t taua = cnt + kNQ * 4;                          // f32 [32]
   static constexpr size_t qcode = taua + kNQ * 4;
   static constexpr size_t qmask = qcode + kNQ * 4;
-  static constexpr size_t bars = qmask + kNQ * 4;  // full[R] empty[R] tfull[A] tempty[A] qbar
+  static constexpr size_t lmax = qmask + kNQ * 4;                        // u32 [32] ordered best score
+  static constexpr size_t stage = lmax + kNQ * 4;                        // f32 [kEpiWarps][32][kQW+1]
+  static constexpr size_t bars = stage + (size_t)kEpiWarps * 32 * (kQW + 1) * 4;  // full[R] empty[R] tfull[A] tempty[A] qbar
   static constexpr size_t nbars = 2 * C::kRing + 2 * kAccStages + 1;
-  static constexpr size_t holder = bars + nbars * 8;
+  static constexpr size_t holder = bars + nbars * 8;  // u32 TMEM base, u32 epilogue-done flag
   static constexpr size_t total = holder + 16;
 };
 
@@ -124,13 +131,69 @@ __device__ __forceinline__ double exact_dot(const void* __restrict__ rows, uint3
   return acc;
 }
 
+// ---- warp selection ---------------------------------------------------------------------------
+// Bitonic sort of one value per lane, descending: lane i ends up with the i-th largest.  15
+// shuffle steps; small code on purpose (see slow_path).
+__device__ __forceinline__ float warp_sort_desc(float x) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      const float y = __shfl_xor_sync(0xffffffffu, x, j2);
+      const bool up = (lane & k2) == 0;
+      const bool lower = (lane & j2) == 0;
+      x = (lower == up) ? fmaxf(x, y) : fminf(x, y);
+    }
+  }
+  return x;
+}
+__device__ __forceinline__ float warp_kth_largest(float x, int k) {
+  return __shfl_sync(0xffffffffu, warp_sort_desc(x), k - 1);
+}
+
+// Running top-kMaxK of a stream of values, kept sorted descending in registers.
+__device__ __forceinline__ void topk_insert(float (&t)[kMaxK], float v) {
+#pragma unroll
+  for (int i = 0; i < kMaxK; ++i) {
+    const float hi = fmaxf(t[i], v);
+    v = fminf(t[i], v);
+    t[i] = hi;
+  }
+}
+// The array is pre-filled with (kMaxK - k) copies of +inf, so that the k-th largest of the inserted
+// values always ends up in the LAST slot: a static register index (a runtime index would push the
+// array into local memory).
+__device__ __forceinline__ void topk_init(float (&t)[kMaxK], int k) {
+#pragma unroll
+  for (int i = 0; i < kMaxK; ++i) t[i] = (i < kMaxK - k) ? INFINITY : -INFINITY;
+}
+__device__ __forceinline__ float topk_kth(const float (&t)[kMaxK]) { return t[kMaxK - 1]; }
+
+// Cross-CTA bound.  Each lane holds the best appended pre-filter scores of up to kGmaxPerLane CTAs
+// for one query.  The lane maxima belong to 32 disjoint CTA groups, i.e. to distinct rows, so the
+// k-th largest of them is a lower bound of the global k-th best pre-filter score (-inf when fewer
+// than k groups have a finite value).
+__device__ __forceinline__ float warp_kth_of_lane_max(const float (&v)[kGmaxPerLane], int k) {
+  float m = v[0];
+#pragma unroll
+  for (int i = 1; i < kGmaxPerLane; ++i) m = fmaxf(m, v[i]);
+  return warp_kth_largest(m, k);
+}
+
+// max on a float in shared memory with integer atomics (works for any sign, +-inf included)
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 // ---- list compaction (one warp, one query) ----------------------------------------------------
 // Keeps every entry that can still be in the exact top-k of the rows this CTA has seen:
 // all entries with pre-filter score >= A_k - 2*eps (A_k = k-th best pre-filter score in the list).
 // If more than kKeep entries sit in that band the band is resolved exactly (fp64) and only the
 // exact top-k stay.  Raises the pass threshold taua[q] accordingly.
 template <bool F32>
-__device__ __noinline__ void compact_list(uint64_t* __restrict__ L, uint32_t* cnt_q, float* taua_q,
+__device__ __forceinline__ void compact_list(uint64_t* __restrict__ L, uint32_t* cnt_q, float* taua_q,
                                           double* __restrict__ scratch, const ScanParams& p, int q,
                                           unsigned long long& n_resolutions) {
   const uint32_t lane = lane_id();
@@ -140,10 +203,15 @@ __device__ __noinline__ void compact_list(uint64_t* __restrict__ L, uint32_t* cn
   const uint64_t e0 = lane < c ? L[lane] : 0ull;
   const uint64_t e1 = lane + 32 < c ? L[lane + 32] : 0ull;
   uint32_t r0 = 0, r1 = 0;
-  for (uint32_t j = 0; j < c; ++j) {
-    const uint64_t kj = L[j];
-    r0 += kj > e0;
-    r1 += kj > e1;
+  for (uint32_t j0 = 0; j0 < c; j0 += 8) {
+    uint64_t kj[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) kj[u] = (j0 + u < c) ? L[j0 + u] : 0ull;  // 0 never outranks an entry
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      r0 += kj[u] > e0;
+      r1 += kj[u] > e1;
+    }
   }
   float cutoff = -INFINITY;
   if (c >= (uint32_t)k) {
@@ -164,7 +232,7 @@ __device__ __noinline__ void compact_list(uint64_t* __restrict__ L, uint32_t* cn
   if (nkeep <= (uint32_t)kKeep) {
     if (lane == 0) {
       *cnt_q = nkeep;
-      if (cutoff > *taua_q) *taua_q = cutoff;
+      atomic_max_f32(taua_q, cutoff);
     }
     __syncwarp();
     return;
@@ -202,9 +270,133 @@ __device__ __noinline__ void compact_list(uint64_t* __restrict__ L, uint32_t* cn
     *cnt_q = (uint32_t)k;
     float t = __fsub_rd(__double2float_rd(exk), p.eps);
     if (cutoff > t) t = cutoff;
-    if (t > *taua_q) *taua_q = t;
+    atomic_max_f32(taua_q, t);
   }
   __syncwarp();
+}
+
+// ---- epilogue state shared by the rare-path functions -------------------------------------------
+struct Epi {
+  uint64_t* keys;     // smem [32][kListCap]
+  double* scratch;    // smem [kEpiWarps][kListCap]
+  uint32_t* cnt;      // smem [32]
+  float* taua;        // smem [32] pass thresholds (pre-filter domain)
+  uint32_t* lmax;     // smem [32] ordered best appended score
+  uint32_t ew;        // epilogue warp 0..kEpiWarps-1: owns queries ew, ew+kEpiWarps, ...
+  uint32_t q0;        // first query column this warp scores (kQW columns)
+  float* stage;       // smem [32][kQW+1]: this warp's scores of the current tile (rare path only)
+  unsigned long long n_app, n_comp, n_res;
+};
+
+// Background refresher (its own warp): keeps raising the pass thresholds from the cross-CTA table
+// gmax[cta][query] while the epilogue warps work.  Lane q handles query q: the k-th largest of the
+// CTAs' best appended scores belongs to k distinct rows (CTAs scan disjoint rows), so it bounds the
+// global k-th best pre-filter score from below; rows under it minus 2*eps can be dropped by every
+// CTA.  Thresholds only ever rise (atomic max), so when an update lands does not matter for
+// correctness.  Small code on purpose (see slow_path).
+__device__ __forceinline__ void refresher_loop(float* taua, const uint32_t* lmax, const volatile uint32_t* done,
+                                               const ScanParams& p) {
+  const uint32_t lane = lane_id();
+  while (*done == 0u) {
+    float t[kMaxK];
+    topk_init(t, p.k);
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < gridDim.x; c0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u)  // 16 rows of the table in flight: one L2 round trip per group
+        v[u] = (c0 + u < gridDim.x) ? __ldcg(p.gmax + (size_t)(c0 + u) * kNQ + lane) : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (c0 + u == blockIdx.x) v[u] = f32_from_ordered(lmax[lane]);
+        topk_insert(t, v[u]);
+      }
+    }
+    const float kth = topk_kth(t);
+    if ((int)lane < p.nq && kth > -INFINITY) atomic_max_f32(&taua[lane], __fsub_rd(kth, 2.0f * p.eps));
+    __nanosleep(1000);
+  }
+}
+
+// The rare path of the epilogue: append the rows that passed, compact full lists, retry.
+// Compact code on purpose (dynamic query index, scores in local memory): it runs for few tiles and
+// must not bloat the instruction footprint of the per-tile fast path.
+template <bool F32>
+__device__ __forceinline__ void slow_path(Epi& e, const ScanParams& p, const uint32_t (&v)[kQW], uint32_t pend,
+                                          uint32_t row) {
+  // Two rules shape this code.  (1) No local memory: the CTA leaves almost no L1 (the 228 KB are
+  // carved out as shared memory), so a stack access is an L2 round trip.  (2) Small code: this
+  // path runs for a handful of tiles, its instructions are fetched cold while L2 and HBM are
+  // saturated by the scan's own traffic, and a straight-line unrolled version was measured at
+  // ~30 us for one pass.  Hence: scores staged in shared memory, real loops, dynamic query index.
+  const uint32_t lane = lane_id();
+  const float eps2 = 2.0f * p.eps;
+  float* st = e.stage + lane * (kQW + 1);
+#pragma unroll
+  for (int j = 0; j < kQW; ++j) st[j] = __uint_as_float(v[j]);
+  __syncwarp();
+  do {
+    // query columns (bit j <-> query q0 + j) with a pending row anywhere in this warp
+    uint32_t wq = pend;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wq |= __shfl_xor_sync(0xffffffffu, wq, o);
+#pragma unroll 1
+    while (wq) {
+      const int j = __ffs(wq) - 1;
+      wq &= wq - 1;
+      const int q = e.q0 + j;
+      const float sq = st[j];
+      bool mine = (pend >> j) & 1u;
+      uint32_t b = __ballot_sync(0xffffffffu, mine);
+      if (__popc(b) > p.k) {
+        // flood: more than k rows of this warp pass.  They are distinct rows, so the k-th best of
+        // them bounds the k-th best overall from below; rows under it minus 2*eps are out for good.
+        const float thr = __fsub_rd(warp_kth_largest(mine ? sq : -INFINITY, p.k), eps2);
+        if (mine && sq < thr) {
+          mine = false;
+          pend &= ~(1u << j);
+        }
+        if (lane == 0) atomic_max_f32(&e.taua[q], thr);
+        b = __ballot_sync(0xffffffffu, mine);
+      }
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&e.cnt[q], (uint32_t)__popc(b));  // one atomic per warp
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const uint32_t slot = base + __popc(b & ((1u << lane) - 1u));
+      const bool put = mine && slot < (uint32_t)kListCap;
+      if (put) {
+        e.keys[q * kListCap + slot] = make_key(sq, row);
+        pend &= ~(1u << j);
+        e.n_app++;
+      }
+      float m = put ? sq : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0 && m > -INFINITY) atomicMax(&e.lmax[q], f32_ordered(m));
+    }
+    named_bar_sync(1, kEpiThreads);
+#pragma unroll 1
+    for (int q = e.ew; q < kNQ; q += kEpiWarps) {
+      if (e.cnt[q] >= (uint32_t)kListCap) {
+        compact_list<F32>(e.keys + q * kListCap, &e.cnt[q], &e.taua[q], e.scratch + e.ew * kListCap, p, q, e.n_res);
+        e.n_comp++;
+      }
+    }
+    named_bar_sync(1, kEpiThreads);
+    // rows that could not be appended (list was full): drop those the new threshold rules out
+    uint32_t rest = pend;
+#pragma unroll 1
+    while (rest) {
+      const int j = __ffs(rest) - 1;
+      rest &= rest - 1;
+      if (!(st[j] >= e.taua[e.q0 + j])) pend &= ~(1u << j);
+    }
+  } while (named_bar_or(1, kEpiThreads, pend != 0));
+  // publish this CTA's best scores for the cross-CTA bound
+  if (lane < kNQ / kEpiWarps) {
+    const int q = e.ew + kEpiWarps * lane;
+    if (q < p.nq) __stcg(p.gmax + (size_t)blockIdx.x * kNQ + q, f32_from_ordered(e.lmax[q]));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,6 +418,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
   float* taua = reinterpret_cast<float*>(sm + S::taua);
   uint32_t* qcode = reinterpret_cast<uint32_t*>(sm + S::qcode);
   uint32_t* qmask = reinterpret_cast<uint32_t*>(sm + S::qmask);
+  uint32_t* lmax = reinterpret_cast<uint32_t*>(sm + S::lmax);
+  float* stage_all = reinterpret_cast<float*>(sm + S::stage);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::bars);
   uint64_t* empty = full + C::kRing;
   uint64_t* tfull = empty + C::kRing;
@@ -243,7 +437,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull[i], 1);   // tcgen05.commit
-      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     mbar_init(qbar, 1);
     fence_barrier_init();
@@ -254,7 +448,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
     taua[t] = t < p.nq ? -INFINITY : INFINITY;  // padded queries never pass
     qcode[t] = t < p.nq ? p.qcode[t] : 0u;
     qmask[t] = t < p.nq ? p.qmask[t] : 0u;
+    lmax[t] = f32_ordered(-INFINITY);
   }
+  if (threadIdx.x == 0) holder[1] = 0u;  // epilogue-done flag for the refresher warp
   if (warp == 1) {
     tmem_alloc(holder, kTmemCols);
     tmem_relinquish();
@@ -263,6 +459,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder;
+  // optional timeline (diagnostics): per CTA {start, first slab landed, last MMA issued,
+  // first tile consumed, last tile consumed, exit} in globaltimer ns
+#define FRS_TL(slot) do { if (p.timeline) p.timeline[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns(); } while (0)
+  if (threadIdx.x == 0) FRS_TL(0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -302,6 +502,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
           const uint32_t ph = (it / C::kRing) & 1;
           mbar_wait(&full[stage], ph);
           tc_fence_after();
+          if (it == 0) FRS_TL(1);
           const uint64_t da = make_desc_sw128(smem_u32(ring + (size_t)stage * kSlabBytes));
           const uint64_t db = make_desc_sw128(smem_u32(qop + s * C::kQSlabBytes));
 #pragma unroll
@@ -311,23 +512,68 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
         }
         tc_commit(&tfull[acc]);  // accumulator complete
       }
+      FRS_TL(2);
+    }
+  } else if (warp == 2 + kEpiWarps) {
+    // ===================== bound refresher =====================
+    if constexpr (!DUMP) {
+      if (gridDim.x >= (uint32_t)p.k) refresher_loop(taua, lmax, reinterpret_cast<volatile uint32_t*>(holder + 1), p);
     }
   } else {
     // ===================== epilogue =====================
-    const uint32_t ew = warp - 2;   // 0..3: which queries this warp compacts
-    const uint32_t lg = warp & 3;   // TMEM lane group this warp may read
-    unsigned long long n_app = 0, n_comp = 0, n_res = 0;
+    Epi e;
+    e.keys = keys; e.scratch = scratch; e.cnt = cnt; e.taua = taua; e.lmax = lmax;
+    e.ew = warp - 2;                // which queries this warp owns (compaction, refresh, hand-over)
+    e.q0 = (e.ew >> 2) * kQW;       // query columns this warp scores
+    e.stage = stage_all + (size_t)e.ew * 32 * (kQW + 1);
+    e.n_app = e.n_comp = e.n_res = 0;
+    const uint32_t lg = warp & 3;   // TMEM lane group (rows) this warp may read
     uint32_t lt = 0;
+    unsigned long long t_wait = 0, t_slow = 0, n_slow = 0;  // diagnostics (timeline mode)
+    // Payload codes are prefetched three tiles ahead.  Under the scan's own traffic (~24 MB of TMA
+    // requests in flight chip-wide) a DRAM access takes a few microseconds, more than one tile
+    // period, and must not sit on the per-tile critical path of the epilogue.
+    auto load_code = [&](uint32_t t) -> uint32_t {
+      const uint32_t r = t * kTileM + lg * 32 + lane;
+      return (t < p.num_tiles && r < p.n) ? __ldg(p.codes + r) : 0xFFFFFFFFu;
+    };
+    if constexpr (!DUMP) {
+      // Bootstrap thresholds from the prep kernel's sample (lane = query): the k-th largest X of
+      // the sample blocks' best fp32 scores means k distinct rows with exact score >= X - eps_s
+      // exist, i.e. with pre-filter score >= X - eps_s - eps; rows under that minus 2*eps are out.
+      if (e.ew == 0) {
+        float t[kMaxK];
+        topk_init(t, p.k);
+        float v[kSampleBlocks];
+#pragma unroll
+        for (int b = 0; b < kSampleBlocks; ++b) v[b] = __ldcg(p.gsample + b * kNQ + lane);
+#pragma unroll
+        for (int b = 0; b < kSampleBlocks; ++b) topk_insert(t, v[b]);
+        const float kth = topk_kth(t);
+        if ((int)lane < p.nq && kth > -INFINITY)
+          atomic_max_f32(&taua[lane], __fsub_rd(__fsub_rd(kth, kEpsSample), 3.0f * p.eps));
+      }
+      named_bar_sync(1, kEpiThreads);
+    }
+    uint32_t code_a = load_code(blockIdx.x);
+    uint32_t code_b = load_code(blockIdx.x + gridDim.x);
+    uint32_t code_c = load_code(blockIdx.x + 2 * gridDim.x);
+
     for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const uint32_t acc = lt % kAccStages;
       const uint32_t aph = (lt / kAccStages) & 1;
       const uint32_t row = tile * kTileM + lg * 32 + lane;
       const bool live = row < p.n;
-      const uint32_t code = live ? __ldg(p.codes + row) : 0xFFFFFFFFu;
+      const uint32_t code = code_a;
+      code_a = code_b;
+      code_b = code_c;
+      code_c = load_code(tile + 3 * gridDim.x);
+      const unsigned long long tw0 = p.timeline ? globaltimer_ns() : 0;
       mbar_wait(&tfull[acc], aph);
+      if (p.timeline) t_wait += globaltimer_ns() - tw0;
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((lg * 32u) << 16) + acc * kNQ, v);
+      uint32_t v[kQW];
+      tmem_ld_32xN<kQW>(tmem_base + ((lg * 32u) << 16) + acc * kNQ + e.q0, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -336,64 +582,67 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
       if constexpr (DUMP) {
         if (live) {
 #pragma unroll
-          for (int q = 0; q < kNQ; ++q) p.dbg_scores[(size_t)q * p.n + row] = __uint_as_float(v[q]);
+          for (int j = 0; j < kQW; ++j) p.dbg_scores[(size_t)(e.q0 + j) * p.n + row] = __uint_as_float(v[j]);
         }
         continue;
       }
 
+      // fast path: compares against the per-query thresholds + payload predicate
       uint32_t pend = 0;
 #pragma unroll
-      for (int q = 0; q < kNQ; ++q) {
-        const bool pass = (__uint_as_float(v[q]) >= taua[q]) && (((code ^ qcode[q]) & qmask[q]) == 0u);
-        pend |= (uint32_t)pass << q;
+      for (int j = 0; j < kQW; ++j) {
+        const int q = e.q0 + j;
+        const bool pass = (__uint_as_float(v[j]) >= taua[q]) && (((code ^ qcode[q]) & qmask[q]) == 0u);
+        pend |= (uint32_t)pass << j;
       }
       if (!live) pend = 0;
 
-      // Rare path: some row of this tile passed some query's threshold.
-      while (named_bar_or(1, 128, pend != 0)) {
-#pragma unroll
-        for (int q = 0; q < kNQ; ++q) {
-          if (pend & (1u << q)) {
-            const uint32_t slot = atomicAdd(&cnt[q], 1u);
-            if (slot < (uint32_t)kListCap) {
-              keys[q * kListCap + slot] = make_key(__uint_as_float(v[q]), row);
-              pend &= ~(1u << q);
-              n_app++;
-            }
-          }
-        }
-        named_bar_sync(1, 128);
-        for (int q = ew; q < kNQ; q += 4) {
-          if (cnt[q] >= (uint32_t)kListCap) {
-            compact_list<F32>(keys + q * kListCap, &cnt[q], &taua[q], scratch + ew * kListCap, p, q, n_res);
-            n_comp++;
-          }
-        }
-        named_bar_sync(1, 128);
-        if (pend) {
-#pragma unroll
-          for (int q = 0; q < kNQ; ++q)
-            if ((pend & (1u << q)) && !(__uint_as_float(v[q]) >= taua[q])) pend &= ~(1u << q);
-        }
+      // rare path: some row of this tile passed some query's threshold
+      if (named_bar_or(1, kEpiThreads, pend != 0)) {
+        const unsigned long long ts0 = p.timeline ? globaltimer_ns() : 0;
+        slow_path<F32>(e, p, v, pend, row);
+        if (p.timeline) { t_slow += globaltimer_ns() - ts0; n_slow++; }
+      }
+
+      if (e.ew == 0 && lane == 0) {
+        if (lt == 0) FRS_TL(3);
+        FRS_TL(4);
       }
     }
 
+    if (e.ew == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(holder + 1) = 1u;  // stop the refresher
+    if (p.timeline && e.ew == 0 && lane == 0) {
+      unsigned long long* ts = p.timeline + (size_t)blockIdx.x * 16;
+      ts[12] = n_slow; ts[13] = t_wait; ts[14] = t_slow; ts[15] = 0;
+    }
     if constexpr (!DUMP) {
-      named_bar_sync(1, 128);
-      for (int q = ew; q < kNQ; q += 4) {
-        compact_list<F32>(keys + q * kListCap, &cnt[q], &taua[q], scratch + ew * kListCap, p, q, n_res);
-        const uint32_t c = cnt[q];
-        uint64_t* dst = p.part_keys + ((size_t)blockIdx.x * kNQ + q) * kKeep;
-        if (lane < c) dst[lane] = keys[q * kListCap + lane];
-        if (lane == 0) p.part_cnt[blockIdx.x * kNQ + q] = c;
+      named_bar_sync(1, kEpiThreads);
+      // Hand the surviving candidates to the merge kernel: every list entry that is not already
+      // ruled out by this CTA's final threshold, unsorted; plus the CTA's best score per query.
+      for (int q = e.ew; q < kNQ; q += kEpiWarps) {
+        const uint32_t c = min(cnt[q], (uint32_t)kListCap);
+        const float t = taua[q];
+        const uint64_t e0 = lane < c ? keys[q * kListCap + lane] : 0ull;
+        const uint64_t e1 = lane + 32 < c ? keys[q * kListCap + lane + 32] : 0ull;
+        const bool k0 = lane < c && key_score(e0) >= t;
+        const bool k1 = lane + 32 < c && key_score(e1) >= t;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+        uint64_t* dst = p.part_keys + ((size_t)blockIdx.x * kNQ + q) * kListCap;
+        const uint32_t below = (1u << lane) - 1u;
+        if (k0) dst[__popc(b0 & below)] = e0;
+        if (k1) dst[__popc(b0) + __popc(b1 & below)] = e1;
+        if (lane == 0) {
+          p.part_cnt[blockIdx.x * kNQ + q] = __popc(b0) + __popc(b1);
+          __stcg(p.gmax + (size_t)blockIdx.x * kNQ + q, f32_from_ordered(lmax[q]));
+        }
       }
-      // per-warp counters -> global (lane sums for n_app, lane 0 for the warp-uniform ones)
+      unsigned long long n_app = e.n_app;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n_app += __shfl_xor_sync(0xffffffffu, n_app, o);
       if (lane == 0) {
         atomicAdd(p.stats + kStatAppended, n_app);
-        atomicAdd(p.stats + kStatCompactions, n_comp);
-        atomicAdd(p.stats + kStatResolutions, n_res);
+        atomicAdd(p.stats + kStatCompactions, e.n_comp);
+        atomicAdd(p.stats + kStatResolutions, e.n_res);
       }
     }
   }
@@ -401,6 +650,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (threadIdx.x == 0) FRS_TL(5);
+#undef FRS_TL
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -432,96 +683,209 @@ __device__ __forceinline__ Best block_max_best(Best v, Best* red /*[8]*/) {
 }
 
 size_t merge_smem_bytes(int nparts) {
-  const size_t ent = (size_t)nparts * kKeep;
-  return ent * 8 /*keys*/ + ent * 8 /*band exact*/ + ent * 4 /*band rows*/ + 256;
+  const size_t ent = (size_t)(nparts > 0 ? nparts : 1) * kListCap;
+  return ent * (8 /*survivor keys*/ + 8 /*band exact*/ + 4 /*band rows*/) + 64;
 }
 
+// up to 4 exact scores at once (same arithmetic and summation order as exact_dot; the loads of all
+// rows are issued before the first use so the DRAM latency is paid once per group)
+template <bool F32>
+__device__ __forceinline__ void exact_dot4(const void* __restrict__ rows, const uint32_t (&r)[4], int n,
+                                           const float* __restrict__ q, double (&out)[4]) {
+  const uint32_t lane = lane_id();
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  float4 b[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) b[c] = __ldg(q4 + lane + 32 * c);
+  if constexpr (F32) {
+    float4 a[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rows) + (size_t)r[i] * kDim);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[i][c] = i < n ? __ldg(a4 + lane + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        acc = fma((double)a[i][c].x, (double)b[c].x, acc);
+        acc = fma((double)a[i][c].y, (double)b[c].y, acc);
+        acc = fma((double)a[i][c].z, (double)b[c].z, acc);
+        acc = fma((double)a[i][c].w, (double)b[c].w, acc);
+      }
+      out[i] = acc;
+    }
+  } else {
+    uint2 a[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint2* a2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(rows) + (size_t)r[i] * kDim);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[i][c] = i < n ? __ldg(a2 + lane + 32 * c) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        acc = fma((double)__uint_as_float(a[i][c].x << 16), (double)b[c].x, acc);
+        acc = fma((double)__uint_as_float(a[i][c].x & 0xFFFF0000u), (double)b[c].y, acc);
+        acc = fma((double)__uint_as_float(a[i][c].y << 16), (double)b[c].z, acc);
+        acc = fma((double)__uint_as_float(a[i][c].y & 0xFFFF0000u), (double)b[c].w, acc);
+      }
+      out[i] = acc;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) out[i] += __shfl_xor_sync(0xffffffffu, out[i], o);
+  }
+}
+
+constexpr uint32_t kRankCountMax = 512;  // above this many entries selection falls back to k rounds
+
+// One CTA per query.
+//  1. coarse cut: k-th largest of the CTAs' best scores (disjoint CTA groups => distinct rows) minus
+//     2*eps; every list entry under it is out.
+//  2. exact cut on the survivors: A_k = k-th best pre-filter key, band = entries >= A_k - 2*eps.
+//  3. band entries are re-scored in fp64 and ordered by (score desc, row asc).
 template <bool F32>
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams p) {
   extern __shared__ __align__(16) uint8_t msm[];
   const int q = blockIdx.x;
-  const int maxent = p.nparts * kKeep;
-  uint64_t* ent = reinterpret_cast<uint64_t*>(msm);
-  double* band_x = reinterpret_cast<double*>(ent + maxent);
+  const int maxent = (p.nparts > 0 ? p.nparts : 1) * kListCap;
+  uint64_t* surv = reinterpret_cast<uint64_t*>(msm);
+  double* band_x = reinterpret_cast<double*>(surv + maxent);
   uint32_t* band_row = reinterpret_cast<uint32_t*>(band_x + maxent);
   __shared__ Best red[kMergeThreads / 32];
-  __shared__ uint32_t n_ent, n_band;
+  __shared__ uint32_t cnt_s[kGmaxPad];
+  __shared__ uint32_t n_surv, n_band;
+  __shared__ uint64_t ak_s;
   const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
   const int k = p.k;
-  if (tid == 0) { n_ent = 0; n_band = 0; }
+  if (tid == 0) { n_surv = 0; n_band = 0; ak_s = 0ull; }
+  if (tid < p.nparts) cnt_s[tid] = p.part_cnt[tid * kNQ + q];
+
+  // 1. coarse cut (computed redundantly by every warp: no block-level exchange needed)
+  float thr0 = -INFINITY;
+  if (p.nparts >= k) {
+    float g[kGmaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kGmaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      g[i] = c < p.nparts ? __ldcg(p.gmax + (size_t)c * kNQ + q) : -INFINITY;
+    }
+    const float kth = warp_kth_of_lane_max(g, k);
+    if (kth > -INFINITY) thr0 = __fsub_rd(kth, 2.0f * p.eps);
+  }
   __syncthreads();
 
-  // gather the surviving entries of every CTA for this query
-  for (int i = tid; i < maxent; i += kMergeThreads) {
-    const int part = i / kKeep, j = i - part * kKeep;
-    if ((uint32_t)j < p.part_cnt[part * kNQ + q]) {
-      const uint64_t key = p.part_keys[((size_t)part * kNQ + q) * kKeep + j];
-      ent[atomicAdd(&n_ent, 1u)] = key;
+  const int total_slots = p.nparts * kListCap;
+  for (int i = tid; i < total_slots; i += kMergeThreads) {
+    const int part = i / kListCap, slot = i % kListCap;
+    if ((uint32_t)slot < cnt_s[part]) {
+      const uint64_t key = __ldg(p.part_keys + ((size_t)part * kNQ + q) * kListCap + slot);
+      if (key_score(key) >= thr0) surv[atomicAdd(&n_surv, 1u)] = key;
     }
   }
   __syncthreads();
-  const uint32_t T = n_ent;
+  const uint32_t S = n_surv;
 
-  // k-th best pre-filter key: k rounds of "largest key below the previous winner"
-  Best prev{~0ull, ~0u};
-  uint64_t ak = 0;
-  for (int r = 0; r < k; ++r) {
-    Best loc{0ull, 0u};
-    for (uint32_t i = tid; i < T; i += kMergeThreads) {
-      const Best c{ent[i], 0u};
-      if (c.hi < prev.hi && loc.hi < c.hi) loc = c;
+  // 2. k-th best pre-filter key among the survivors
+  if (S >= (uint32_t)k) {
+    if (S <= kRankCountMax) {
+      for (uint32_t i = tid; i < S; i += kMergeThreads) {
+        const uint64_t mine = surv[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < S; ++j) rank += surv[j] > mine;
+        if (rank == (uint32_t)(k - 1)) ak_s = mine;
+      }
+    } else {
+      uint64_t prev = ~0ull;
+      for (int r = 0; r < k; ++r) {
+        Best loc{0ull, 0u};
+        for (uint32_t i = tid; i < S; i += kMergeThreads) {
+          const uint64_t c = surv[i];
+          if (c < prev && loc.hi < c) loc.hi = c;
+        }
+        prev = block_max_best(loc, red).hi;
+      }
+      if (tid == 0) ak_s = prev;
     }
-    const Best m = block_max_best(loc, red);
-    if (m.hi == 0ull) break;
-    prev = m;
-    ak = m.hi;
   }
-  const float cutoff = (T >= (uint32_t)k) ? __fsub_rd(key_score(ak), 2.0f * p.eps) : -INFINITY;
-
-  // the band: everything that may still be in the exact top-k
-  for (uint32_t i = tid; i < T; i += kMergeThreads) {
-    const uint64_t key = ent[i];
-    if (key_score(key) >= cutoff) band_row[atomicAdd(&n_band, 1u)] = key_row(key);
+  __syncthreads();
+  const float thr1 = S >= (uint32_t)k ? __fsub_rd(key_score(ak_s), 2.0f * p.eps) : -INFINITY;
+  for (uint32_t i = tid; i < S; i += kMergeThreads) {
+    const uint64_t key = surv[i];
+    if (key_score(key) >= thr1) band_row[atomicAdd(&n_band, 1u)] = key_row(key);
   }
   __syncthreads();
   const uint32_t NB = n_band;
 
-  // exact fp64 scores of the band, one warp per entry
+  // 3. exact fp64 scores of the band: each warp takes groups of 4 rows
   const float* qv = p.qrec + (size_t)q * kDim;
-  for (uint32_t j = tid >> 5; j < NB; j += kMergeThreads / 32) {
-    const double ex = exact_dot<F32>(p.rows, band_row[j], qv);
-    if ((tid & 31) == 0) band_x[j] = ex;
+  for (uint32_t j0 = warp * 4; j0 < NB; j0 += (kMergeThreads / 32) * 4) {
+    uint32_t r[4];
+    const int n = (int)min(4u, NB - j0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = band_row[min(j0 + i, NB - 1)];
+    double x[4];
+    exact_dot4<F32>(p.rows, r, n, qv, x);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n) band_x[j0 + i] = x[i];
+    }
   }
   __syncthreads();
   if (tid == 0 && p.stats) atomicAdd(p.stats + kStatRescored, (unsigned long long)NB);
 
   // exact top-k, ordered (score desc, row asc)
-  Best pb{~0ull, ~0u};
-  bool exhausted = false;
-  for (int r = 0; r < k; ++r) {
-    Best loc{0ull, 0u};
-    if (!exhausted) {
+  const uint32_t nout = NB < (uint32_t)k ? NB : (uint32_t)k;
+  if (NB <= kRankCountMax) {
+    for (uint32_t i = tid; i < NB; i += kMergeThreads) {
+      const double xi = band_x[i];
+      const uint32_t ri = band_row[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < NB; ++j) {
+        const double xj = band_x[j];
+        rank += (xj > xi) || (xj == xi && band_row[j] < ri);
+      }
+      if (rank < (uint32_t)k) {
+        const size_t o = (size_t)q * k + rank;
+        if (p.out_s64) p.out_s64[o] = xi;
+        if (p.out_s32) p.out_s32[o] = (float)xi;
+        p.out_ids[o] = p.base + (int64_t)ri;
+      }
+    }
+  } else {
+    Best pb{~0ull, ~0u};
+    for (uint32_t r = 0; r < nout; ++r) {
+      Best loc{0ull, 0u};
       for (uint32_t i = tid; i < NB; i += kMergeThreads) {
         const Best c{f64_ordered(band_x[i]), ~band_row[i]};
         if (best_less(c, pb) && best_less(loc, c)) loc = c;
       }
-    }
-    const Best m = block_max_best(loc, red);
-    if (m.hi == 0ull && m.lo == 0u) exhausted = true;
-    if (tid == 0) {
-      const size_t o = (size_t)q * k + r;
-      if (!exhausted) {
-        const double s = f64_from_ordered(m.hi);
-        if (p.out_s64) p.out_s64[o] = s;
-        if (p.out_s32) p.out_s32[o] = (float)s;
+      const Best m = block_max_best(loc, red);
+      if (tid == 0) {
+        const size_t o = (size_t)q * k + r;
+        const double sc = f64_from_ordered(m.hi);
+        if (p.out_s64) p.out_s64[o] = sc;
+        if (p.out_s32) p.out_s32[o] = (float)sc;
         p.out_ids[o] = p.base + (int64_t)(~m.lo);
-      } else {
-        if (p.out_s64) p.out_s64[o] = -INFINITY;
-        if (p.out_s32) p.out_s32[o] = -INFINITY;
-        p.out_ids[o] = -1;
       }
+      pb = m;
     }
-    pb = m;
+  }
+  for (uint32_t r = nout + tid; r < (uint32_t)k; r += kMergeThreads) {
+    const size_t o = (size_t)q * k + r;
+    if (p.out_s64) p.out_s64[o] = -INFINITY;
+    if (p.out_s32) p.out_s32[o] = -INFINITY;
+    p.out_ids[o] = -1;
   }
 }
 
@@ -583,14 +947,27 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// one warp per query slot (32 slots); slots >= nq are zero filled
+// Query preparation + bootstrap sample.  kSampleBlocks blocks of 32 warps.  Every block normalises
+// the 32 query slots (one warp per slot; slots >= nq are zero) into shared memory; block 0 also writes
+// the MMA operand, the fp32 record copy, the predicate copies and resets the per-search tables.
+// Then warp w of block b scores one sampled row against all queries (lane = query) in fp32 and the
+// block publishes its best matching score per query: k distinct rows that good are known to exist
+// before the scan starts, so its first tiles do not have to accept everything.
+constexpr int kQsStride = kDim + 1;  // +1: lanes read different queries at the same element
 template <bool F32>
-__global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(const float* __restrict__ q, const uint32_t* __restrict__ code,
-                                    const uint32_t* __restrict__ mask, int nq, void* __restrict__ qop,
-                                    float* __restrict__ qrec, uint32_t* __restrict__ qcode,
-                                    uint32_t* __restrict__ qmask, unsigned long long* stats) {
+__global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
+    const float* __restrict__ q, const uint32_t* __restrict__ code, const uint32_t* __restrict__ mask, int nq,
+    void* __restrict__ qop, float* __restrict__ qrec, uint32_t* __restrict__ qcode, uint32_t* __restrict__ qmask,
+    unsigned long long* stats, float* __restrict__ gmax, float* __restrict__ gsample,
+    const void* __restrict__ rows, const uint32_t* __restrict__ codes, uint32_t n) {
+  extern __shared__ float qs[];  // [32][kQsStride]
+  __shared__ uint32_t smax[kNQ], s_code[kNQ], s_mask[kNQ];
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < kStatSlots && stats) stats[threadIdx.x] = 0ull;
+  const bool first = blockIdx.x == 0;
+  if (first) {
+    if (threadIdx.x < kStatSlots && stats) stats[threadIdx.x] = 0ull;
+    for (int i = threadIdx.x; i < kNQ * kGmaxPad; i += blockDim.x) gmax[i] = -INFINITY;
+  }
   float x[12];
   float ss = 0.f;
   if (slot < nq) {
@@ -607,21 +984,65 @@ __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(const float* __r
   const float nrm = sqrtf(ss);
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
-    float y = nrm > 0.f ? x[i] / nrm : 0.f;
+    const float y = nrm > 0.f ? x[i] / nrm : 0.f;
     const size_t o = (size_t)slot * kDim + lane + 32 * i;
+    float rec;
     if constexpr (F32) {
-      qrec[o] = y;
-      reinterpret_cast<float*>(qop)[o] = round_tf32(y);
+      rec = y;
+      if (first) reinterpret_cast<float*>(qop)[o] = round_tf32(y);
     } else {
       const __nv_bfloat16 b = __float2bfloat16_rn(y);
-      reinterpret_cast<__nv_bfloat16*>(qop)[o] = b;
-      qrec[o] = __bfloat162float(b);
+      rec = __bfloat162float(b);
+      if (first) reinterpret_cast<__nv_bfloat16*>(qop)[o] = b;
     }
+    if (first) qrec[o] = rec;
+    qs[slot * kQsStride + lane + 32 * i] = rec;
   }
   if (lane == 0) {
-    qcode[slot] = slot < nq ? code[slot] : 0u;
-    qmask[slot] = slot < nq ? mask[slot] : 0u;
+    const uint32_t c = slot < nq ? code[slot] : 0u, m = slot < nq ? mask[slot] : 0u;
+    s_code[slot] = c;
+    s_mask[slot] = m;
+    smax[slot] = f32_ordered(-INFINITY);
+    if (first) {
+      qcode[slot] = c;
+      qmask[slot] = m;
+    }
   }
+  __syncthreads();
+
+  // sampled row of this warp: a stride over the whole store (or the first rows of a small one)
+  const uint32_t total = kSampleBlocks * kSampleRows;
+  const uint32_t idx = blockIdx.x * kSampleRows + slot;
+  const uint32_t r = n >= total ? idx * (n / total) : idx;
+  if (r < n) {
+    const uint32_t rc = __ldg(codes + r);
+    const float* qv = qs + lane * kQsStride;
+    float acc = 0.f;
+    if constexpr (F32) {
+      const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rows) + (size_t)r * kDim);
+#pragma unroll 8
+      for (int i = 0; i < kDim / 4; ++i) {
+        const float4 a = __ldg(a4 + i);  // same address in every lane: one broadcast transaction
+        acc = fmaf(a.x, qv[4 * i], acc);
+        acc = fmaf(a.y, qv[4 * i + 1], acc);
+        acc = fmaf(a.z, qv[4 * i + 2], acc);
+        acc = fmaf(a.w, qv[4 * i + 3], acc);
+      }
+    } else {
+      const uint2* a2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(rows) + (size_t)r * kDim);
+#pragma unroll 8
+      for (int i = 0; i < kDim / 4; ++i) {
+        const uint2 a = __ldg(a2 + i);
+        acc = fmaf(__uint_as_float(a.x << 16), qv[4 * i], acc);
+        acc = fmaf(__uint_as_float(a.x & 0xFFFF0000u), qv[4 * i + 1], acc);
+        acc = fmaf(__uint_as_float(a.y << 16), qv[4 * i + 2], acc);
+        acc = fmaf(__uint_as_float(a.y & 0xFFFF0000u), qv[4 * i + 3], acc);
+      }
+    }
+    if (lane < nq && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u) atomicMax(&smax[lane], f32_ordered(acc));
+  }
+  __syncthreads();
+  if (threadIdx.x < kNQ) gsample[blockIdx.x * kNQ + threadIdx.x] = f32_from_ordered(smax[threadIdx.x]);
 }
 
 // one warp per row
@@ -707,9 +1128,26 @@ cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_sha
 
 cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, const uint32_t* mask,
                                 int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
-                                unsigned long long* stats, cudaStream_t st) {
-  if (f32) prep_queries_kernel<true><<<1, 32 * kNQ, 0, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats);
-  else prep_queries_kernel<false><<<1, 32 * kNQ, 0, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats);
+                                unsigned long long* stats, float* gmax, float* gsample, const void* rows,
+                                const uint32_t* codes, uint32_t n, cudaStream_t st) {
+  const size_t smem = (size_t)kNQ * kQsStride * sizeof(float);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    e = cudaFuncSetAttribute(prep_queries_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(prep_queries_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  if (f32)
+    prep_queries_kernel<true><<<kSampleBlocks, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
+                                                                     gmax, gsample, rows, codes, n);
+  else
+    prep_queries_kernel<false><<<kSampleBlocks, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
+                                                                      gmax, gsample, rows, codes, n);
   return cudaGetLastError();
 }
 

@@ -13,10 +13,20 @@ constexpr int kSlabBytes = kTileM * 128;  // 128 rows x 128 B: one SWIZZLE_128B 
 constexpr int kListCap = 64;    // per-query candidate list capacity inside a CTA
 constexpr int kKeep = 32;       // most entries a list keeps after a compaction
 constexpr int kMaxK = 16;       // largest `limit` supported              reference main.py:215
-constexpr int kAccStages = 8;   // TMEM accumulator ring (8 x 32 columns)
+constexpr int kAccStages = 16;  // TMEM accumulator ring (16 x 32 columns = all 512)
 constexpr int kTmemCols = kAccStages * kNQ;
-constexpr int kScanThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kEpiWarps = 8;      // epilogue warps: 4 TMEM lane groups x 2 query-column groups
+constexpr int kQW = kNQ / (kEpiWarps / 4);  // query columns per epilogue warp (16)
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kScanThreads = 64 + kEpiThreads + 32;  // warp0 TMA, warp1 MMA, epilogue warps, bound refresher
 constexpr int kMergeThreads = 256;
+constexpr int kGmaxPerLane = 5;                 // cross-CTA bound table: up to 160 CTAs
+constexpr int kGmaxPad = 32 * kGmaxPerLane;     // floats per query
+
+// bootstrap sample scored by the prep kernel: kSampleBlocks blocks x kSampleRows rows
+constexpr int kSampleBlocks = 32;
+constexpr int kSampleRows = 32;
+constexpr float kEpsSample = 3.0e-5f;  // |fp32 FMA-chain score - fp64 score| bound (384 terms)
 
 // bound on |tensor-core pre-filter score - fp64 score| for unit-norm rows and queries
 constexpr float kEpsBF16 = 3.0e-5f;  // exact products, fp32 accumulation of 384 terms
@@ -35,15 +45,19 @@ struct ScanParams {
   int nq;                  // live queries (<= 32)
   int k;                   // top-k (<= kMaxK)
   float eps;               // pre-filter error bound
-  uint64_t* part_keys;     // [grid, 32, kKeep] surviving (approx score, row) keys per CTA
+  uint64_t* part_keys;     // [grid, 32, kListCap] surviving (approx score, row) keys per CTA, unsorted
   uint32_t* part_cnt;      // [grid, 32]
+  float* gmax;             // [kGmaxPad, 32] best appended pre-filter score per (CTA, query)
+  const float* gsample;    // [kSampleBlocks, 32] best fp32 score per (sample block, query), or -inf
   float* dbg_scores;       // DUMP mode only: [32, n]
   unsigned long long* stats;  // [kStatSlots]
+  unsigned long long* timeline;  // diagnostics: [grid, 8] globaltimer stamps, or null
 };
 
 struct MergeParams {
   const uint64_t* part_keys;
   const uint32_t* part_cnt;
+  const float* gmax;   // [kGmaxPad, 32] final best pre-filter score per (CTA, query)
   int nparts;
   const void* rows;
   const float* qrec;
@@ -68,9 +82,11 @@ cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_sha
                                 float* out_s32, int64_t* out_ids, cudaStream_t st);
 // queries [nq,384] fp32 -> qop (MMA operand, bf16 or tf32-rounded fp32, zero padded to 32 rows),
 // qrec (fp32 record copy), qcode/qmask copies padded to 32
+// also scores a strided sample of the stored rows against the prepared queries (bootstrap bound)
 cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, const uint32_t* mask,
                                 int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
-                                unsigned long long* stats, cudaStream_t st);
+                                unsigned long long* stats, float* gmax, float* gsample, const void* rows,
+                                const uint32_t* codes, uint32_t n, cudaStream_t st);
 // rows [n,384] fp32 -> L2-normalised storage rows (+ codes) at dst row offset
 cudaError_t launch_store_rows(bool f32, const float* vecs, const uint32_t* codes, int64_t n,
                               void* rows_dst, uint32_t* codes_dst, cudaStream_t st);

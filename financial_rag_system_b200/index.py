@@ -161,6 +161,21 @@ class VectorIndex:
         torch.cuda.current_stream(self.device).synchronize()
         return out
 
+    def set_profiling(self, mode: int) -> None:
+        check(self._lib.frs_index_set_profiling(self._h, int(mode)))
+
+    def read_profile(self) -> dict:
+        """{'n', 'prep_ms', 'scan_ms', 'merge_ms'}: per-kernel CUDA-event time summed over the
+        searches recorded since the last call (profiling mode >= 1)."""
+        buf = (C.c_double * 4)()
+        check(self._lib.frs_index_read_profile(self._h, buf))
+        return {"n": int(buf[0]), "prep_ms": buf[1], "scan_ms": buf[2], "merge_ms": buf[3]}
+
+    def read_timeline(self, n_ctas: int) -> np.ndarray:
+        out = np.zeros((n_ctas, 16), dtype=np.uint64)
+        check(self._lib.frs_index_read_timeline(self._h, _ptr(out), n_ctas))
+        return out
+
     def last_stats(self) -> dict:
         buf = (C.c_int64 * 6)()
         check(self._lib.frs_index_last_stats(self._h, buf))

@@ -146,6 +146,16 @@ int frs_index_debug_scores(frs_index* idx, const float* dev_queries, int nq, flo
  * [4] scan grid size, [5] kernels launched by the last search call */
 int frs_index_last_stats(frs_index* idx, int64_t* host_out6);
 
+/* Profiling (off by default).  mode 1: CUDA events are recorded on the caller's stream around each
+ * kernel of a search (prep, scan, merge); mode 2: additionally the scan kernel stamps a per-CTA
+ * timeline.  read_profile synchronises and returns {searches, prep ms, scan ms, merge ms} summed
+ * over the searches recorded since the last read (at most the last 256). */
+int frs_index_set_profiling(frs_index* idx, int mode);
+int frs_index_read_profile(frs_index* idx, double* host_out4);
+/* [n_ctas, 16] globaltimer ns: start, first slab landed, last MMA issued, first tile consumed,
+ * last tile consumed, exit, then stamps of the first rare-path invocation (diagnostics) */
+int frs_index_read_timeline(frs_index* idx, uint64_t* host_out, int n_ctas);
+
 /* ---- encoders: replace SentenceTransformer.encode / CrossEncoder.predict -
  * BertModel forward (transformers/models/bert/modeling_bert.py) for the two
  * checkpoints of main.py:84,90.  Declared here; see encoder section of DESIGN.md. */

@@ -72,7 +72,7 @@ def diag_search(dtype, n, nq=32, k=15, filt=True, grid=0):
     return ok_ids
 
 
-def bench(dtype, n, iters=20):
+def bench(dtype, n, iters=20, nomatch=False):
     g = torch.Generator(device="cuda").manual_seed(9)
     ix = VectorIndex(n, dtype=dtype)
     chunk = 1 << 18
@@ -83,6 +83,9 @@ def bench(dtype, n, iters=20):
     q = torch.randn((32, 384), generator=g, device="cuda")
     qc = torch.zeros(32, dtype=torch.int32, device="cuda")
     qm = torch.full((32,), 0x80000000 - (1 << 32), dtype=torch.int64).to(torch.int32).cuda()
+    if nomatch:  # a ticker no row has: zero candidates -> raw streaming rate of the scan
+        qc = torch.full((32,), 0xFFFFFF, dtype=torch.int32, device="cuda")
+        qm = torch.full((32,), 0x80FFFFFF - (1 << 32), dtype=torch.int64).to(torch.int32).cuda()
     for _ in range(3):
         ix.search(q, qc, qm, 15)
     torch.cuda.synchronize()
@@ -94,16 +97,32 @@ def bench(dtype, n, iters=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     bytes_ = n * 384 * (4 if dtype == "f32" else 2) + n * 4
-    print(f"[bench {dtype} n={n}] {ms*1e3:.1f} us/batch  {bytes_/ms/1e6:.0f} GB/s  {32/ms*1e3:.0f} QPS  stats={ix.last_stats()}", flush=True)
+    print(f"[bench {dtype} n={n} nomatch={nomatch}] {ms*1e3:.1f} us/batch  {bytes_/ms/1e6:.0f} GB/s  {32/ms*1e3:.0f} QPS  stats={ix.last_stats()}", flush=True)
+    ix.set_profiling(2)
+    for _ in range(iters):
+        ix.search(q, qc, qm, 15)
+    torch.cuda.synchronize()
+    pr = ix.read_profile()
+    nn = max(pr["n"], 1)
+    print(f"   per-kernel (events): prep {pr['prep_ms']/nn*1e3:.1f} us  scan {pr['scan_ms']/nn*1e3:.1f} us  merge {pr['merge_ms']/nn*1e3:.1f} us"
+          f"  -> scan {bytes_/(pr['scan_ms']/nn)/1e6:.0f} GB/s", flush=True)
+    grid = ix.last_stats()["grid"]
+    tl = ix.read_timeline(grid).astype(np.int64)
+    t0 = tl[:, 0].min()
+    rel = (tl[:, :6] - t0) / 1e3
+    names = ["start", "first_slab", "last_mma", "first_tile_done", "last_tile_done", "exit"]
+    for j, nm in enumerate(names):
+        print(f"   timeline {nm:>16}: min {rel[:, j].min():8.1f}  median {np.median(rel[:, j]):8.1f}  max {rel[:, j].max():8.1f} us", flush=True)
+    print(f"   epilogue warp0 per CTA (median): slow-path calls={np.median(tl[:, 12]):.0f}  wait_tfull={np.median(tl[:, 13])/1e3:.1f} us"
+          f"  in_slow_path={np.median(tl[:, 14])/1e3:.1f} us  in_refresh={np.median(tl[:, 15])/1e3:.1f} us", flush=True)
+    ix.set_profiling(0)
     ix.close()
 
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     steps = [
-        lambda: diag_scores("bf16", 1000),
         lambda: diag_scores("bf16", 50000),
-        lambda: diag_scores("f32", 1000),
         lambda: diag_scores("f32", 50000),
         lambda: diag_search("bf16", 1000),
         lambda: diag_search("bf16", 100000),
@@ -112,7 +131,7 @@ if __name__ == "__main__":
         lambda: diag_search("f32", 100000),
         lambda: diag_search("f32", 100000, filt=False, grid=3),
         lambda: bench("bf16", 1_000_000),
-        lambda: bench("f32", 1_000_000),
+        lambda: bench("bf16", 1_000_000, nomatch=True),
         lambda: bench("bf16", 10_000_000),
     ]
     for s in steps:
