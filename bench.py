@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the retrieval hot path (BASELINE.json `metric`):
+QPS of exact top-15 cosine search over 10M x 384-d bf16 chunks, 32-query batches, on 1/2/4/8 B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one 32-query batch searched over the whole corpus (10M rows in total, sharded over the
+N ranks: strong scaling, as BASELINE.json quotes the metric).  One JSON line is printed by rank 0.
+
+  value      device-timed whole-job QPS, queries resident in HBM when the timed region starts
+  e2e        the same batches through the host entry point (numpy in, numpy out): pinned H2D of the
+             queries + predicates and D2H of ids/scores inside every timed step
+  roofline   scan kernel only: algorithmic bytes (rows*768 + rows*4 per launch) / CUDA-event time of
+             the scan kernel (library-side events on the launching stream, second timed region)
+  cpu_baseline / --impl reference
+             the reference's CPU arithmetic for this step (float32 dot + full argsort per query,
+             oracle.search_oracle.as_shipped_search — a restatement: qdrant-client is not installed
+             here, see oracle/search_oracle.py) on a bounded 1M-row sample, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_ROWS = int(os.environ.get("FRS_BENCH_ROWS", 10_000_000))
+NQ, K, DIM = 32, 15, 384
+N_TICKERS = 500
+CPU_SAMPLE_ROWS = 1_000_000
+TICKER_MASK = 0x80FFFFFF
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic SEC-style corpus: 1024 topic centroids + noise (norm 0.3), ticker ~ Zipf(1.1) over 500
+# --------------------------------------------------------------------------------------------------
+def zipf_probs(n=N_TICKERS, a=1.1):
+    p = 1.0 / np.arange(1, n + 1) ** a
+    return p / p.sum()
+
+
+def gen_chunk_cuda(torch, gen, cent, probs_t, m):
+    cid = torch.randint(0, cent.shape[0], (m,), generator=gen, device=cent.device)
+    x = cent[cid] + (0.3 / DIM ** 0.5) * torch.randn((m, DIM), generator=gen, device=cent.device)
+    codes = torch.multinomial(probs_t, m, replacement=True, generator=gen).to(torch.int32)
+    return x, codes
+
+
+def clocks_sampler(stop, out, gpu_index):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [s.strip() for s in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.1)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    mx = max(int(s[1]) for s in samples if s[1].isdigit()) if any(s[1].isdigit() for s in samples) else None
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's arithmetic for one step on a bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_step_time(rows, codes, queries, q_ticker, steps, warmup):
+    from oracle import search_oracle as so
+
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for qi in range(queries.shape[0]):
+            so.as_shipped_search(rows, queries[qi], codes == q_ticker[qi], K)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.median(times))
+
+
+def cpu_sample_data(n_rows=CPU_SAMPLE_ROWS, seed=1234):
+    from oracle import search_oracle as so
+
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((1024, DIM)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    cid = rng.integers(0, 1024, n_rows)
+    rows = cent[cid] + (0.3 / DIM ** 0.5) * rng.standard_normal((n_rows, DIM), dtype=np.float32)
+    rows = so.l2_normalize_f32(rows)
+    codes = rng.choice(N_TICKERS, n_rows, p=zipf_probs()).astype(np.uint32)
+    src = rng.integers(0, n_rows, NQ)
+    queries = rows[src] + 0.02 * rng.standard_normal((NQ, DIM)).astype(np.float32)
+    return rows, codes, queries, codes[src]
+
+
+def cpu_baseline(steps=2, warmup=1):
+    cores = len(os.sched_getaffinity(0))
+    rows, codes, queries, qt = cpu_sample_data()
+    t = cpu_step_time(rows, codes, queries, qt, steps, warmup)
+    scale = TOTAL_ROWS / CPU_SAMPLE_ROWS
+    return {
+        "value": NQ / (t * scale), "unit": "queries/s", "cores": cores, "kind": "port",
+        "sample": f"{CPU_SAMPLE_ROWS} of {TOTAL_ROWS} rows per 32-query step (float32 dot + full argsort per query, "
+                  f"numpy/OpenBLAS, {cores} threads); step time scaled x{scale:g} (the scan is linear in rows)",
+        "sample_step_s": t,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    # size the per-step sample so that the whole run (W + K steps) stays within ~2.5 minutes
+    rows, codes, queries, qt = cpu_sample_data(50_000)
+    per_row = cpu_step_time(rows, codes, queries, qt, 1, 1) / 50_000
+    budget_s = 150.0
+    sample_rows = int(min(CPU_SAMPLE_ROWS, max(50_000, budget_s / ((args.steps + args.warmup) * per_row))))
+    rows, codes, queries, qt = cpu_sample_data(sample_rows)
+    t = cpu_step_time(rows, codes, queries, qt, args.steps, args.warmup)
+    scale = TOTAL_ROWS / sample_rows
+    qps = NQ / (t * scale)
+    line = {
+        "impl": "reference", "metric": "exact top-15 cosine search QPS (384-d, 10M chunks, 32-query batches)",
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * scale * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_rows} of {TOTAL_ROWS} rows per step, step time scaled x{scale:g} (linear scan); "
+                                   "restatement of qdrant-client local-mode exact search (float32 dot + argsort), "
+                                   f"numpy/OpenBLAS on {cores} threads"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"{TOTAL_ROWS} x 384 bf16 chunk store, 32-query batches, exact cosine top-15, per-query ticker filter",
+        "rows_total": TOTAL_ROWS, "rows_per_gpu": TOTAL_ROWS // n_gpus, "dim": DIM, "batch": NQ, "k": K,
+        "filter": f"ticker == T, T ~ Zipf(1.1) over {N_TICKERS} tickers (reference main.py:218-223)",
+        "corpus": "1024 unit centroids + noise of norm 0.3, L2-normalised, generated on device (seed 7)",
+        "parallelism": f"rows sharded over {n_gpus} GPU(s), one NCCL all-gather of 32x15 (score,id) per batch" if n_gpus > 1 else "1 GPU",
+        "l2": "inputs larger than L2 (7.7 GB corpus per step vs 126 MB L2)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from financial_rag_system_b200.index import VectorIndex
+    from financial_rag_system_b200.sharded import ShardedIndex, shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- build this rank's shard (never materialised on the host) ----
+    start, length = shard_range(TOTAL_ROWS, rank, world)
+    ix = VectorIndex(length, dtype="bf16", device=local_rank, base=start)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    cent = torch.randn((1024, DIM), generator=gen, device=dev)
+    cent = cent / cent.norm(dim=1, keepdim=True)
+    probs_t = torch.tensor(zipf_probs(), dtype=torch.float32, device=dev)
+    gen_rows = torch.Generator(device=dev).manual_seed(1000 + rank)
+    first_rows = first_codes = None
+    chunk = 1 << 18
+    for s in range(0, length, chunk):
+        m = min(chunk, length - s)
+        x, codes = gen_chunk_cuda(torch, gen_rows, cent, probs_t, m)
+        ix.add(x, codes)
+        if s == 0 and rank == 0:
+            first_rows, first_codes = x[:NQ].clone(), codes[:NQ].clone()
+    # queries: perturbed corpus rows of rank 0 with their tickers, identical on every rank
+    q = torch.zeros((NQ, DIM), dtype=torch.float32, device=dev)
+    qc = torch.zeros((NQ,), dtype=torch.int32, device=dev)
+    if rank == 0:
+        gq = torch.Generator(device=dev).manual_seed(11)
+        q = first_rows + 0.02 * torch.randn((NQ, DIM), generator=gq, device=dev)
+        qc = first_codes
+    if world > 1:
+        dist.broadcast(q, 0)
+        dist.broadcast(qc, 0)
+    qm = torch.full((NQ,), TICKER_MASK - (1 << 32), dtype=torch.int64).to(torch.int32).to(dev)
+    sh = ShardedIndex(ix, rank, world) if world > 1 else None
+
+    def step():
+        if sh is None:
+            return ix.search(q, qc, qm, K)
+        return sh.search_async(q, qc, qm, K)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+    barrier()
+
+    # ---- timed region A: value ----
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+    if rank == 0:
+        th.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    last = None
+    for _ in range(args.steps):
+        last = step()
+    if sh is not None:
+        torch.cuda.current_stream(dev).wait_stream(sh._side)
+    e1.record()
+    barrier()
+    stop.set()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ids, scores = last.wait() if sh is not None else last
+    assert int(ids[0, 0].item()) == 0, "query 0 is a perturbed copy of global row 0"
+
+    # ---- timed region B: per-kernel events (roofline of the scan kernel) ----
+    ix.set_profiling(1)
+    barrier()
+    for _ in range(min(args.steps, 200)):
+        step()
+    barrier()
+    prof = ix.read_profile()
+    ix.set_profiling(0)
+    scan_ms = prof["scan_ms"] / max(prof["n"], 1)
+    launches_per_step = ix.last_stats()["launches"] + (1 if world > 1 else 0)  # + cross-shard merge kernel
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed step ----
+    qh, qch, qmh = q.cpu().numpy(), qc.cpu().numpy().astype(np.uint32), np.full(NQ, TICKER_MASK, np.uint32)
+    e2e_steps = args.steps
+    if sh is None:
+        for _ in range(3):
+            ix.search(qh, qch, qmh, K)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hi, hs = ix.search(qh, qch, qmh, K)
+        e2e_s = time.perf_counter() - t0
+        assert np.array_equal(hi, ids.cpu().numpy())
+    else:
+        pin_q = torch.from_numpy(qh).pin_memory()
+        pin_c = torch.from_numpy(qch.astype(np.int64)).to(torch.int32).pin_memory()
+        pin_m = torch.from_numpy(qmh.astype(np.int64)).to(torch.int32).pin_memory()
+        out_i = torch.empty((NQ, K), dtype=torch.int64).pin_memory()
+        out_s = torch.empty((NQ, K), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            dq, dc, dm = pin_q.to(dev, non_blocking=True), pin_c.to(dev, non_blocking=True), pin_m.to(dev, non_blocking=True)
+            i_, s_ = sh.search(dq, dc, dm, K)
+            out_i.copy_(i_, non_blocking=True)
+            out_s.copy_(s_, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = length * (DIM * 2 + 4)
+        achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if int(tj.get("rows", -1)) == length:
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        cb = cpu_baseline() if world == 1 else None
+        line = {
+            "metric": "exact top-15 cosine search QPS (384-d, 10M chunks, 32-query batches)",
+            "value": NQ * args.steps / (ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": NQ * e2e_steps / e2e_s, "unit": "queries/s",
+                    "h2d_bytes_per_step": NQ * DIM * 4 + 2 * NQ * 4, "d2h_bytes_per_step": NQ * K * (4 + 8)},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "scan_kernel<bf16>", "kernel_ms": scan_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "per_step_kernel_ms": {"prep": prof["prep_ms"] / max(prof["n"], 1), "scan": scan_ms,
+                                                "merge": prof["merge_ms"] / max(prof["n"], 1)}},
+            "clocks": summarize_clocks(samples),
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "frs_index_search_host": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "frs_index_search_local": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "frs_merge_shards": (_int, [_int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
+    "frs_merge_shards_packed": (_int, [_int, _vp, _int, _int, _int, _vp, _vp, _vp]),
     "frs_index_last_queries": (_int, [_vp, _vp, _vp]),
     "frs_index_debug_scores": (_int, [_vp, _vp, _int, _vp, _vp]),
     "frs_index_last_stats": (_int, [_vp, C.POINTER(_i64)]),

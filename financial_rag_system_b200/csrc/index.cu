@@ -509,8 +509,21 @@ extern "C" int frs_merge_shards(int device, const double* dev_scores64, const in
   if (!dev_scores64 || !dev_ids || !dev_out_scores || !dev_out_ids) return set_err(FRS_E_INVALID, "null pointer argument");
   if (n_shards < 1 || nq < 1 || k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "bad shape");
   CU_TRY(cudaSetDevice(device));
-  CU_TRY(launch_merge_shards(dev_scores64, dev_ids, n_shards, nq, k, dev_out_scores, dev_out_ids,
+  CU_TRY(launch_merge_shards(dev_scores64, dev_ids, n_shards, nq, k, (size_t)nq * k, dev_out_scores, dev_out_ids,
                              (cudaStream_t)stream));
+  return FRS_OK;
+}
+
+// Same merge over the exchange buffer of ShardedIndex: [n_shards][2][nq][k] 64-bit words, plane 0 =
+// fp64 score bits, plane 1 = int64 global ids (one all-gather moves both).
+extern "C" int frs_merge_shards_packed(int device, const int64_t* dev_packed, int n_shards, int nq, int k,
+                                       float* dev_out_scores, int64_t* dev_out_ids, void* stream) {
+  if (!dev_packed || !dev_out_scores || !dev_out_ids) return set_err(FRS_E_INVALID, "null pointer argument");
+  if (n_shards < 1 || nq < 1 || k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "bad shape");
+  CU_TRY(cudaSetDevice(device));
+  const size_t plane = (size_t)nq * k;
+  CU_TRY(launch_merge_shards(reinterpret_cast<const double*>(dev_packed), dev_packed + plane, n_shards, nq, k,
+                             2 * plane, dev_out_scores, dev_out_ids, (cudaStream_t)stream));
   return FRS_OK;
 }
 

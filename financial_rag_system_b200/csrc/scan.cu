@@ -544,11 +544,14 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
       if (e.ew == 0) {
         float t[kMaxK];
         topk_init(t, p.k);
-        float v[kSampleBlocks];
+#pragma unroll 1
+        for (int b0 = 0; b0 < kSampleBlocks; b0 += 32) {
+          float v[32];
 #pragma unroll
-        for (int b = 0; b < kSampleBlocks; ++b) v[b] = __ldcg(p.gsample + b * kNQ + lane);
+          for (int b = 0; b < 32; ++b) v[b] = __ldcg(p.gsample + (b0 + b) * kNQ + lane);
 #pragma unroll
-        for (int b = 0; b < kSampleBlocks; ++b) topk_insert(t, v[b]);
+          for (int b = 0; b < 32; ++b) topk_insert(t, v[b]);
+        }
         const float kth = topk_kth(t);
         if ((int)lane < p.nq && kth > -INFINITY)
           atomic_max_f32(&taua[lane], __fsub_rd(__fsub_rd(kth, kEpsSample), 3.0f * p.eps));
@@ -893,22 +896,22 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
 // cross-shard merge: [n_shards, nq, k] exact (fp64 score, global id) -> [nq, k]; one warp per query
 // ---------------------------------------------------------------------------------------------
 __global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_t* __restrict__ ids,
-                                    int n_shards, int nq, int k, float* __restrict__ out_s32,
-                                    int64_t* __restrict__ out_ids) {
+                                    int n_shards, int nq, int k, size_t shard_stride,
+                                    float* __restrict__ out_s32, int64_t* __restrict__ out_ids) {
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
   const int total = n_shards * k;
   // each lane owns candidates lane, lane+32, ... ; rank = number of strictly better candidates
   for (int c = lane; c < total; c += 32) {
     const int sh = c / k, j = c - sh * k;
-    const size_t off = ((size_t)sh * nq + q) * k + j;
+    const size_t off = (size_t)sh * shard_stride + (size_t)q * k + j;
     const int64_t id = ids[off];
     if (id < 0) continue;
     const double s = s64[off];
     int rank = 0;
     for (int d = 0; d < total; ++d) {
       const int sh2 = d / k, j2 = d - sh2 * k;
-      const size_t off2 = ((size_t)sh2 * nq + q) * k + j2;
+      const size_t off2 = (size_t)sh2 * shard_stride + (size_t)q * k + j2;
       const int64_t id2 = ids[off2];
       if (id2 < 0) continue;
       const double s2 = s64[off2];
@@ -923,7 +926,7 @@ __global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_
   int valid = 0;
   for (int c = lane; c < total; c += 32) {
     const int sh = c / k, j = c - sh * k;
-    valid += ids[((size_t)sh * nq + q) * k + j] >= 0;
+    valid += ids[(size_t)sh * shard_stride + (size_t)q * k + j] >= 0;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
@@ -950,24 +953,55 @@ __device__ __forceinline__ float round_tf32(float x) {
 // Query preparation + bootstrap sample.  kSampleBlocks blocks of 32 warps.  Every block normalises
 // the 32 query slots (one warp per slot; slots >= nq are zero) into shared memory; block 0 also writes
 // the MMA operand, the fp32 record copy, the predicate copies and resets the per-search tables.
-// Then warp w of block b scores one sampled row against all queries (lane = query) in fp32 and the
-// block publishes its best matching score per query: k distinct rows that good are known to exist
-// before the scan starts, so its first tiles do not have to accept everything.
+// Each block then scores kSampleRows sampled rows against all queries in fp32 and publishes its best
+// matching score per query: k distinct rows that good are known to exist before the scan starts, so
+// its first tiles do not have to accept everything.  The sampled rows are fetched (one DRAM latency,
+// overlapped with the normalisation) into shared memory; warp w scores half of row w/2, lane = query.
 constexpr int kQsStride = kDim + 1;  // +1: lanes read different queries at the same element
+constexpr int kPrepRowElems = kSampleRows * kDim / (32 * kNQ);  // row elements fetched per thread (6)
+constexpr size_t kPrepSmem = ((size_t)kNQ * kQsStride + (size_t)kSampleRows * kDim + 32 * 32) * sizeof(float);
 template <bool F32>
 __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
     const float* __restrict__ q, const uint32_t* __restrict__ code, const uint32_t* __restrict__ mask, int nq,
     void* __restrict__ qop, float* __restrict__ qrec, uint32_t* __restrict__ qcode, uint32_t* __restrict__ qmask,
     unsigned long long* stats, float* __restrict__ gmax, float* __restrict__ gsample,
     const void* __restrict__ rows, const uint32_t* __restrict__ codes, uint32_t n) {
-  extern __shared__ float qs[];  // [32][kQsStride]
-  __shared__ uint32_t smax[kNQ], s_code[kNQ], s_mask[kNQ];
+  static_assert(kSampleRows * 2 == 32, "scoring maps warp w to (row w/2, half w%2)");
+  static_assert(kSampleRows * kDim % (32 * kNQ) == 0, "row elements must split evenly over the block");
+  extern __shared__ __align__(16) float psm[];
+  float* rs = psm;                              // [kSampleRows][kDim] sampled rows widened to fp32
+  float* qs = rs + kSampleRows * kDim;          // [32][kQsStride] prepared queries
+  float* part = qs + kNQ * kQsStride;           // [32 warps][32 queries] partial dot products
+  __shared__ uint32_t smax[kNQ], s_code[kNQ], s_mask[kNQ], s_rcode[kSampleRows];
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool first = blockIdx.x == 0;
+
+  // 1. sampled rows: a stride over the whole store (or the first rows of a small one)
+  const uint32_t total = kSampleBlocks * kSampleRows;
+  const uint32_t stride = n >= total ? n / total : 1u;
+  float rv[kPrepRowElems];
+#pragma unroll
+  for (int e = 0; e < kPrepRowElems; ++e) {
+    const uint32_t idx = threadIdx.x + 32 * kNQ * e;
+    const uint32_t j = idx / kDim, c = idx - j * kDim;
+    const uint32_t r = (blockIdx.x * kSampleRows + j) * stride;
+    float v = 0.f;
+    if (r < n) {
+      if constexpr (F32) v = __ldg(reinterpret_cast<const float*>(rows) + (size_t)r * kDim + c);
+      else v = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rows) + (size_t)r * kDim + c) << 16);
+    }
+    rv[e] = v;
+  }
+  if (threadIdx.x < kSampleRows) {
+    const uint32_t r = (blockIdx.x * kSampleRows + threadIdx.x) * stride;
+    s_rcode[threadIdx.x] = r < n ? __ldg(codes + r) : 0xFFFFFFFFu;
+  }
   if (first) {
     if (threadIdx.x < kStatSlots && stats) stats[threadIdx.x] = 0ull;
     for (int i = threadIdx.x; i < kNQ * kGmaxPad; i += blockDim.x) gmax[i] = -INFINITY;
   }
+
+  // 2. normalise the queries
   float x[12];
   float ss = 0.f;
   if (slot < nq) {
@@ -1008,38 +1042,33 @@ __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
       qmask[slot] = m;
     }
   }
+#pragma unroll
+  for (int e = 0; e < kPrepRowElems; ++e) rs[threadIdx.x + 32 * kNQ * e] = rv[e];
   __syncthreads();
 
-  // sampled row of this warp: a stride over the whole store (or the first rows of a small one)
-  const uint32_t total = kSampleBlocks * kSampleRows;
-  const uint32_t idx = blockIdx.x * kSampleRows + slot;
-  const uint32_t r = n >= total ? idx * (n / total) : idx;
-  if (r < n) {
-    const uint32_t rc = __ldg(codes + r);
-    const float* qv = qs + lane * kQsStride;
+  // 3. score: warp -> (row, half of the 384 elements), lane -> query
+  {
+    const int j = slot >> 1, h = slot & 1;
+    const float4* r4 = reinterpret_cast<const float4*>(rs + j * kDim) + h * (kDim / 8);
+    const float* qv = qs + lane * kQsStride + h * (kDim / 2);
     float acc = 0.f;
-    if constexpr (F32) {
-      const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rows) + (size_t)r * kDim);
 #pragma unroll 8
-      for (int i = 0; i < kDim / 4; ++i) {
-        const float4 a = __ldg(a4 + i);  // same address in every lane: one broadcast transaction
-        acc = fmaf(a.x, qv[4 * i], acc);
-        acc = fmaf(a.y, qv[4 * i + 1], acc);
-        acc = fmaf(a.z, qv[4 * i + 2], acc);
-        acc = fmaf(a.w, qv[4 * i + 3], acc);
-      }
-    } else {
-      const uint2* a2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(rows) + (size_t)r * kDim);
-#pragma unroll 8
-      for (int i = 0; i < kDim / 4; ++i) {
-        const uint2 a = __ldg(a2 + i);
-        acc = fmaf(__uint_as_float(a.x << 16), qv[4 * i], acc);
-        acc = fmaf(__uint_as_float(a.x & 0xFFFF0000u), qv[4 * i + 1], acc);
-        acc = fmaf(__uint_as_float(a.y << 16), qv[4 * i + 2], acc);
-        acc = fmaf(__uint_as_float(a.y & 0xFFFF0000u), qv[4 * i + 3], acc);
-      }
+    for (int i = 0; i < kDim / 8; ++i) {
+      const float4 a = r4[i];  // same address in every lane: broadcast
+      acc = fmaf(a.x, qv[4 * i], acc);
+      acc = fmaf(a.y, qv[4 * i + 1], acc);
+      acc = fmaf(a.z, qv[4 * i + 2], acc);
+      acc = fmaf(a.w, qv[4 * i + 3], acc);
     }
-    if (lane < nq && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u) atomicMax(&smax[lane], f32_ordered(acc));
+    part[slot * 32 + lane] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kSampleRows * 32) {
+    const int j = threadIdx.x >> 5;  // row; lane = query
+    const float sc = part[(2 * j) * 32 + lane] + part[(2 * j + 1) * 32 + lane];
+    const uint32_t rc = s_rcode[j];
+    if (lane < nq && rc != 0xFFFFFFFFu && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u)
+      atomicMax(&smax[lane], f32_ordered(sc));
   }
   __syncthreads();
   if (threadIdx.x < kNQ) gsample[blockIdx.x * kNQ + threadIdx.x] = f32_from_ordered(smax[threadIdx.x]);
@@ -1121,8 +1150,8 @@ cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st) {
 }
 
 cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
-                                float* out_s32, int64_t* out_ids, cudaStream_t st) {
-  merge_shards_kernel<<<nq, 32, 0, st>>>(s64, ids, n_shards, nq, k, out_s32, out_ids);
+                                size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st) {
+  merge_shards_kernel<<<nq, 32, 0, st>>>(s64, ids, n_shards, nq, k, shard_stride, out_s32, out_ids);
   return cudaGetLastError();
 }
 
@@ -1130,7 +1159,7 @@ cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, 
                                 int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
                                 unsigned long long* stats, float* gmax, float* gsample, const void* rows,
                                 const uint32_t* codes, uint32_t n, cudaStream_t st) {
-  const size_t smem = (size_t)kNQ * kQsStride * sizeof(float);
+  const size_t smem = kPrepSmem;
   static bool configured[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

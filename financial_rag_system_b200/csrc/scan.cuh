@@ -24,8 +24,8 @@ constexpr int kGmaxPerLane = 5;                 // cross-CTA bound table: up to 
 constexpr int kGmaxPad = 32 * kGmaxPerLane;     // floats per query
 
 // bootstrap sample scored by the prep kernel: kSampleBlocks blocks x kSampleRows rows
-constexpr int kSampleBlocks = 32;
-constexpr int kSampleRows = 32;
+constexpr int kSampleBlocks = 64;
+constexpr int kSampleRows = 16;   // per block: 4 warps x 4 rows
 constexpr float kEpsSample = 3.0e-5f;  // |fp32 FMA-chain score - fp64 score| bound (384 terms)
 
 // bound on |tensor-core pre-filter score - fp64 score| for unit-norm rows and queries
@@ -78,8 +78,9 @@ size_t merge_smem_bytes(int nparts);
 cudaError_t launch_scan(bool f32, bool dump, int grid, const CUtensorMap& tmap_rows,
                         const CUtensorMap& tmap_q, const ScanParams& p, cudaStream_t st);
 cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st);
+// shard_stride: elements between consecutive shards in both arrays (nq*k when they are dense)
 cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
-                                float* out_s32, int64_t* out_ids, cudaStream_t st);
+                                size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st);
 // queries [nq,384] fp32 -> qop (MMA operand, bf16 or tf32-rounded fp32, zero padded to 32 rows),
 // qrec (fp32 record copy), qcode/qmask copies padded to 32
 // also scores a strided sample of the stored rows against the prepared queries (bootstrap bound)

@@ -193,3 +193,16 @@ def merge_shards(scores64: torch.Tensor, ids: torch.Tensor, k: int):
     check(_lib.lib().frs_merge_shards(dev.index or 0, _ptr(scores64.contiguous()), _ptr(ids.contiguous()), n_shards, nq, k,
                                       _ptr(out_s), _ptr(out_i), _stream_ptr(dev)))
     return out_i, out_s
+
+
+def merge_shards_packed(packed: torch.Tensor, k: int):
+    """[n_shards, 2, nq, k] int64 exchange buffer (plane 0 fp64 score bits, plane 1 ids) -> merged
+    ([nq,k] ids, [nq,k] float32 scores), on device."""
+    n_shards, two, nq, kk = packed.shape
+    assert two == 2 and kk == k and packed.dtype == torch.int64 and packed.is_contiguous()
+    dev = packed.device
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    check(_lib.lib().frs_merge_shards_packed(dev.index or 0, _ptr(packed), n_shards, nq, k, _ptr(out_s), _ptr(out_i),
+                                             _stream_ptr(dev)))
+    return out_i, out_s

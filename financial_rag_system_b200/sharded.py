@@ -1,0 +1,138 @@
+"""ShardedIndex — corpus (row) sharding of the chunk store over the GPUs of one box.
+
+One process per GPU (torch.distributed).  Rank r owns the contiguous global row range
+[base_r, base_r + len_r): brute force reads every row whatever the filter, so contiguous placement
+is balanced.  A search is
+
+    local pass    every rank scans its shard for all queries -> exact local top-k as
+                  (float64 score, int64 global id)                       [CUDA: prep/scan/merge]
+    exchange      ONE all-gather of world * nq * k * 16 bytes (46 KB at 8 x 32 x 15)   [NCCL]
+    final merge   [world, nq, k] -> [nq, k] by (score desc, id asc) on every rank      [CUDA]
+
+The per-shard lists are exact, so the result is identical to a single-shard search of the whole
+corpus whatever the number of shards.  The exchange + final merge of batch i run on a side stream
+and overlap the local pass of batch i+1 (`search_async`).
+
+The reference has no counterpart (one Qdrant server, main.py:215-239); this is north-star item (3).
+`local_search` / `merge` are injectable so that the host-side logic (partitioning, gather layout,
+ordering) is exercised on CPU under the gloo backend in tests/test_sharded_cpu.py.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total_rows: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous partition: the first (total % world) shards get one extra row."""
+    q, r = divmod(int(total_rows), int(world))
+    start = rank * q + min(rank, r)
+    return start, q + (1 if rank < r else 0)
+
+
+class PendingSearch:
+    """Result of search_async: tensors are valid once `ready` has been waited on."""
+
+    def __init__(self, ids: torch.Tensor, scores: torch.Tensor, ready):
+        self.ids, self.scores, self._ready = ids, scores, ready
+
+    def wait(self):
+        if self._ready is not None:
+            self._ready.synchronize()
+        return self.ids, self.scores
+
+
+class ShardedIndex:
+    def __init__(self, local_index, rank: int, world: int, group=None,
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 device: Optional[torch.device] = None):
+        """local_index: a VectorIndex whose base is this shard's first global row (or any object
+        when local_search/merge are injected)."""
+        self.local = local_index
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.device = device if device is not None else getattr(local_index, "device", torch.device("cpu"))
+        self._local_search = local_search or self._cuda_local_search
+        self._merge = merge or self._cuda_merge
+        self._side = None
+        self._slot = 0
+        self._slot_free = [None, None]  # event: the side stream is done with this slot's buffers
+        self._bufs = {}
+
+    # -- default (CUDA) implementations -----------------------------------------------------------
+    def _cuda_local_search(self, q, qc, qm, k, out_scores64, out_ids):
+        self.local.search_local(q, qc, qm, k, out_scores64, out_ids)
+
+    @staticmethod
+    def _cuda_merge(packed, k):
+        from .index import merge_shards_packed
+
+        return merge_shards_packed(packed, k)
+
+    # -- buffers ------------------------------------------------------------------------------------
+    def _buffers(self, nq: int, k: int, slot: int):
+        key = (nq, k, slot)
+        if key not in self._bufs:
+            # one int64 tensor carries both halves of the candidates: plane 0 = fp64 score bits,
+            # plane 1 = global ids; the local pass writes straight into the planes
+            loc = torch.empty((2, nq, k), dtype=torch.int64, device=self.device)
+            gat = torch.empty((self.world, 2, nq, k), dtype=torch.int64, device=self.device)
+            self._bufs[key] = (loc, gat)
+        return self._bufs[key]
+
+    def _exchange_and_merge(self, loc: torch.Tensor, gat: torch.Tensor, k: int):
+        if self.world > 1:
+            # output viewed as the concatenation of the per-rank inputs along dim 0 (what gloo expects;
+            # NCCL accepts both forms)
+            dist.all_gather_into_tensor(gat.view(-1, gat.shape[2], gat.shape[3]), loc, group=self.group)
+        else:
+            gat.copy_(loc.unsqueeze(0))
+        return self._merge(gat, k)
+
+    def _local_pass(self, q, qc, qm, k, loc):
+        self._local_search(q, qc, qm, k, loc[0].view(torch.float64), loc[1])
+
+    # -- public -------------------------------------------------------------------------------------
+    def search(self, queries, q_code, q_mask, k: int = 15):
+        """Synchronous-in-stream sharded search; every rank must call it with the same queries.
+        Returns (ids int64 [nq,k] global, scores float32 [nq,k]) on every rank."""
+        q, qc, qm = self._prep(queries, q_code, q_mask)
+        loc, gat = self._buffers(q.shape[0], k, 0)
+        self._local_pass(q, qc, qm, k, loc)
+        return self._exchange_and_merge(loc, gat, k)
+
+    def search_async(self, queries, q_code, q_mask, k: int = 15) -> PendingSearch:
+        """Pipelined variant (CUDA only): the exchange and final merge run on a side stream so the
+        next call's local pass overlaps them.  Alternates between two buffer sets."""
+        assert self.device.type == "cuda", "search_async needs CUDA streams"
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        q, qc, qm = self._prep(queries, q_code, q_mask)
+        slot = self._slot
+        self._slot ^= 1
+        loc, gat = self._buffers(q.shape[0], k, slot)
+        main = torch.cuda.current_stream(self.device)
+        # the buffers of this slot were last used two calls ago on the side stream
+        if self._slot_free[slot] is not None:
+            main.wait_event(self._slot_free[slot])
+        self._local_pass(q, qc, qm, k, loc)
+        done_local = torch.cuda.Event()
+        done_local.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(done_local)
+            ids, scores = self._exchange_and_merge(loc, gat, k)
+            ready = torch.cuda.Event()
+            ready.record(self._side)
+        self._slot_free[slot] = ready
+        return PendingSearch(ids, scores, ready)
+
+    def _prep(self, queries, q_code, q_mask):
+        q = torch.as_tensor(queries).to(device=self.device, dtype=torch.float32).contiguous()
+        qc = torch.as_tensor(q_code).to(device=self.device)
+        qm = torch.as_tensor(q_mask).to(device=self.device)
+        if qc.dtype != torch.int32:
+            qc = qc.to(torch.int64).to(torch.int32)
+        if qm.dtype != torch.int32:
+            qm = qm.to(torch.int64).to(torch.int32)
+        return q, qc.contiguous(), qm.contiguous()

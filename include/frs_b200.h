@@ -133,6 +133,10 @@ int frs_index_search_local(frs_index* idx, const float* dev_queries, const uint3
                            int64_t* dev_out_ids, void* stream);
 int frs_merge_shards(int device, const double* dev_scores64, const int64_t* dev_ids, int n_shards,
                      int nq, int k, float* dev_out_scores, int64_t* dev_out_ids, void* stream);
+/* same, over the exchange buffer [n_shards][2][nq][k] of 64-bit words (plane 0 = fp64 score bits,
+ * plane 1 = int64 ids) so that one all-gather moves both halves of the candidates */
+int frs_merge_shards_packed(int device, const int64_t* dev_packed, int n_shards, int nq, int k,
+                            float* dev_out_scores, int64_t* dev_out_ids, void* stream);
 
 /* the prepared (normalised, storage-dtype-rounded) queries of the last search,
  * widened to fp32: what the scores are dot products with.  [FRS_MAX_BATCH, 384] */
