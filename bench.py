@@ -56,6 +56,29 @@ def gen_chunk_cuda(torch, gen, cent, probs_t, m):
 
 
 def clocks_sampler(stop, out, gpu_index):
+    """Samples SM clock and throttle reasons during the timed region: NVML when importable (fast),
+    else the nvidia-smi query of B200_PROFILING.md."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber devices; the bench uses physical order when it is unset
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        R = pynvml
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            flag = lambda bit: "Active" if (r & bit) else "Not Active"  # noqa: E731
+            out.append([str(sm), str(mx), flag(R.nvmlClocksThrottleReasonHwSlowdown), flag(R.nvmlClocksThrottleReasonHwThermalSlowdown),
+                        flag(R.nvmlClocksThrottleReasonSwThermalSlowdown), flag(R.nvmlClocksThrottleReasonSwPowerCap)])
+            stop.wait(0.01)
+        return
+    except Exception:
+        pass
     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     while not stop.is_set():
