@@ -55,42 +55,61 @@ def gen_chunk_cuda(torch, gen, cent, probs_t, m):
     return x, codes
 
 
-def clocks_sampler(stop, out, gpu_index):
+class ClockSampler:
     """Samples SM clock and throttle reasons during the timed region: NVML when importable (fast),
     else the nvidia-smi query of B200_PROFILING.md."""
-    try:
-        import pynvml
 
-        pynvml.nvmlInit()
-        # CUDA_VISIBLE_DEVICES may renumber devices; the bench uses physical order when it is unset
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
-        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-        R = pynvml
-        while not stop.is_set():
-            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
-                else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            flag = lambda bit: "Active" if (r & bit) else "Not Active"  # noqa: E731
-            out.append([str(sm), str(mx), flag(R.nvmlClocksThrottleReasonHwSlowdown), flag(R.nvmlClocksThrottleReasonHwThermalSlowdown),
-                        flag(R.nvmlClocksThrottleReasonSwThermalSlowdown), flag(R.nvmlClocksThrottleReasonSwPowerCap)])
-            stop.wait(0.01)
-        return
-    except Exception:
-        pass
-    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    while not stop.is_set():
+
+    def __init__(self, gpu_index):
+        self.samples, self.stop, self.gpu_index = [], threading.Event(), gpu_index
+        self.nv = self.h = self.mx = None
         try:
-            r = subprocess.run(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                               capture_output=True, text=True, timeout=5)
-            f = [s.strip() for s in r.stdout.strip().split(",")]
-            if len(f) >= 6:
-                out.append(f)
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            parts = [p for p in vis.split(",") if p]
+            phys = int(parts[gpu_index]) if gpu_index < len(parts) and parts[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+
+    def sample(self):
+        try:
+            if self.nv is not None:
+                nv = self.nv
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                f = lambda bit: "Active" if (r & bit) else "Not Active"  # noqa: E731
+                self.samples.append([str(sm), str(self.mx), f(nv.nvmlClocksThrottleReasonHwSlowdown),
+                                     f(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                     f(nv.nvmlClocksThrottleReasonSwThermalSlowdown), f(nv.nvmlClocksThrottleReasonSwPowerCap)])
+            else:
+                r = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
         except Exception:
             pass
-        stop.wait(0.1)
+
+    def _loop(self):
+        while not self.stop.is_set():
+            self.sample()
+            self.stop.wait(0.01 if self.nv is not None else 0.1)
+
+    def start(self):
+        self.thread.start()
+
+    def finish(self):
+        self.stop.set()
+        return self.samples
 
 
 def summarize_clocks(samples):
@@ -253,10 +272,9 @@ def run_ours(args):
     barrier()
 
     # ---- timed region A: value ----
-    stop, samples = threading.Event(), []
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+    sampler = ClockSampler(local_rank)
     if rank == 0:
-        th.start()
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -266,8 +284,10 @@ def run_ours(args):
     if sh is not None:
         torch.cuda.current_stream(dev).wait_stream(sh._side)
     e1.record()
+    if rank == 0:
+        sampler.sample()  # the GPU is still working through the queued steps: at least one sample under load
     barrier()
-    stop.set()
+    samples = sampler.finish()
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
