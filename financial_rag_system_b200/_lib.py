@@ -58,6 +58,17 @@ PROTOTYPES = {
     "frs_index_set_profiling": (_int, [_vp, _int]),
     "frs_index_read_profile": (_int, [_vp, C.POINTER(C.c_double)]),
     "frs_index_read_timeline": (_int, [_vp, _vp, _int]),
+    "frs_encoder_create": (_int, [_int, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),
+    "frs_encoder_destroy": (_int, [_vp]),
+    "frs_encoder_max_tokens": (_int, [_vp]),
+    "frs_encoder_embed": (_int, [_vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "frs_encoder_embed_host": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
+    "frs_encoder_score_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "frs_encoder_score_pairs_host": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
+    "frs_encoder_last_hidden": (_int, [_vp, _vp, _int, _vp]),
+    "frs_encoder_debug_read": (_int, [_vp, _int, _vp, _i64, _vp]),
+    "frs_encoder_set_profiling": (_int, [_vp, _int]),
+    "frs_encoder_read_profile": (_int, [_vp, C.POINTER(C.c_double)]),
 }
 
 _lib = None

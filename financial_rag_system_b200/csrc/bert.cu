@@ -1,0 +1,773 @@
+// bert.cu — sm_100a kernels of the two BERT encoders (bge-small-en-v1.5, ms-marco-MiniLM-L-6-v2).
+//
+// What they replace, in transformers/models/bert/modeling_bert.py (the arithmetic that
+// SentenceTransformer.encode / CrossEncoder.predict run for reference main.py:148,213,245 and
+// main2.py:166,171):
+//   embed_ln_kernel        BertEmbeddings.forward            :102-112
+//   gemm_kernel<QKV>       BertSelfAttention q/k/v Linear    :179-181   (one fused [1152,384] GEMM)
+//   attention_kernel       softmax(QK^T/sqrt(32) + mask) V   :115-140, :192-205  (varlen, no padding)
+//   gemm_kernel<ResLN>     BertSelfOutput / BertOutput       :294-298, :352-356  (bias+residual+LayerNorm)
+//   gemm_kernel<Gelu>      BertIntermediate (erf GELU)       :339-342
+//   pool_normalize_kernel  sentence-transformers Pooling(cls|mean) + Normalize
+//   ce_head_kernel         BertPooler + classifier           :462-468, :1111-1124
+//
+// Every GEMM is tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM) fed by TMA into
+// SWIZZLE_128B shared-memory slabs; warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM
+// allocation), warps 2..9 epilogue / softmax (a thread owns one token row = one TMEM lane).
+#include <math.h>
+
+#include "bert.cuh"
+#include "common.cuh"
+
+namespace frs {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float bf16_round(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float gelu_erf(float x) {  // modeling_bert.py:339-342, hidden_act="gelu"
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// positions + embeddings
+// ---------------------------------------------------------------------------------------------
+__global__ void positions_kernel(const int32_t* __restrict__ cu, int n_seqs, int32_t* __restrict__ pos) {
+  const int s = blockIdx.x;
+  if (s >= n_seqs) return;
+  const int t0 = cu[s], t1 = cu[s + 1];
+  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) pos[t] = t - t0;
+}
+
+// one warp per token: 384 = 3 x (32 lanes x float4)
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ type_ids,
+                const int32_t* __restrict__ pos_ids, int M, int vocab, const float* __restrict__ word,
+                const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ x) {
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= M) return;
+  int id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const int tt = type_ids ? (type_ids[tok] != 0) : 0;
+  int ps = pos_ids[tok];
+  ps = ps < 0 ? 0 : (ps >= kMaxSeq ? kMaxSeq - 1 : ps);
+  const float4* w = reinterpret_cast<const float4*>(word + (size_t)id * kHid);
+  const float4* pp = reinterpret_cast<const float4*>(pos + (size_t)ps * kHid);
+  const float4* ty = reinterpret_cast<const float4*>(type + (size_t)tt * kHid);
+  float v[12];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float4 a = __ldg(w + lane + 32 * i), b = __ldg(pp + lane + 32 * i), c = __ldg(ty + lane + 32 * i);
+    v[4 * i + 0] = a.x + b.x + c.x;
+    v[4 * i + 1] = a.y + b.y + c.y;
+    v[4 * i + 2] = a.z + b.z + c.z;
+    v[4 * i + 3] = a.w + b.w + c.w;
+    sum += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
+  }
+  const float mean = warp_sum(sum) * (1.0f / kHid);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const float d = v[i] - mean;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / kHid) + eps);
+  uint2* out = reinterpret_cast<uint2*>(x + (size_t)tok * kHid);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    const float y0 = (v[4 * i + 0] - mean) * rstd * g.x + b.x;
+    const float y1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+    const float y2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z;
+    const float y3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+    out[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM  C[M,N] = A[M,K] . W[N,K]^T  with fused epilogues
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmEpiThreads = 32 * kGemmEpiWarps;
+constexpr int kGemmThreads = 64 + kGemmEpiThreads;
+constexpr int kNSub = 192;  // N of one tcgen05.mma / rows of one weight TMA box
+
+template <int BN>
+struct GemmCfg {
+  static_assert(BN == 192 || BN == 384, "tile N is 192 or 384");
+  static constexpr int kStageA = kBM * 128;    // 128 rows x 64 bf16
+  static constexpr int kStageB = BN * 128;     // BN rows x 64 bf16
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = BN == 192 ? 5 : 3;
+  static constexpr int kAcc = BN == 192 ? 2 : 1;  // TMEM accumulator stages (2 x 192 or 1 x 384 columns)
+  static constexpr int kNSplit = BN / kNSub;
+  static constexpr int kColsPerThread = BN / 2;   // two epilogue warps share a TMEM lane quarter
+  static constexpr int kRing = kStages * kStage;
+  static constexpr int kParF = kRing;                  // fp32 params: bias[1536] | gamma[384] | beta[384]
+  static constexpr int kStat = kParF + (1536 + 768) * 4;  // float2 [2 parity][2 halves][128 rows]
+  static constexpr int kBars = kStat + 2 * 2 * 128 * 8;
+  static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc) * 8;
+  static constexpr int kTotal = kHolder + 16;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmParams p) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = sm;
+  float* sbias = reinterpret_cast<float*>(sm + C::kParF);
+  float* sgamma = sbias + 1536;
+  float* sbeta = sgamma + 384;
+  float2* sstat = reinterpret_cast<float2*>(sm + C::kStat);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + C::kBars);
+  uint64_t* empty = full + C::kStages;
+  uint64_t* tfull = empty + C::kStages;
+  uint64_t* tempty = tfull + C::kAcc;
+  uint32_t* holder = reinterpret_cast<uint32_t*>(sm + C::kHolder);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int nt_count = p.N / BN;
+  const int ksteps = p.K / 64;
+  const int num_tiles = p.num_mtiles * nt_count;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < C::kAcc; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kGemmEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
+  if constexpr (EPI == kEpiResLN) {
+    for (int i = threadIdx.x; i < kHid; i += blockDim.x) {
+      sgamma[i] = p.gamma[i];
+      sbeta[i] = p.beta[i];
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / nt_count, nt = tile % nt_count;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const uint32_t stage = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&empty[stage], ph ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::kStage);
+          uint8_t* sa = ring + (size_t)stage * C::kStage;
+          tma_load_2d(sa, &tmap_a, &full[stage], ks * 64, mt * kBM, kEvictNormal);
+#pragma unroll
+          for (int s = 0; s < C::kNSplit; ++s)
+            tma_load_2d(sa + C::kStageA + s * (kNSub * 128), &tmap_b, &full[stage], ks * 64,
+                        nt * BN + s * kNSub, kEvictLast);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1u, kBM, kNSub);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt % C::kAcc;
+        const uint32_t aph = (lt / C::kAcc) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const uint32_t stage = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full[stage], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + (size_t)stage * C::kStage);
+          const uint64_t da = make_desc_sw128(sa);
+#pragma unroll
+          for (int s = 0; s < C::kNSplit; ++s) {
+            const uint64_t db = make_desc_sw128(sa + C::kStageA + s * (kNSub * 128));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma<false>(d_tmem + s * kNSub, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0));
+          }
+          tc_commit(&empty[stage]);
+        }
+        tc_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const uint32_t quarter = warp & 3;           // TMEM lanes 32*quarter .. +32 are visible to this warp
+    const uint32_t half = (warp - 2) >> 2;       // which half of the tile's columns
+    const uint32_t row = quarter * 32 + lane;    // row within the tile
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int mt = tile / nt_count, nt = tile % nt_count;
+      const uint32_t acc = lt % C::kAcc;
+      const uint32_t aph = (lt / C::kAcc) & 1;
+      const int grow = mt * kBM + (int)row;
+      const bool live = grow < p.M;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN + half * C::kColsPerThread;
+      uint32_t v[32];
+      if constexpr (EPI == kEpiQKV || EPI == kEpiGelu) {
+#pragma unroll 1
+        for (int c = 0; c < C::kColsPerThread / 32; ++c) {
+          const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // global output column
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (!live) continue;
+          const float* bs = sbias + col;
+          if (EPI == kEpiQKV && col >= 2 * kHid) {
+            // value projection: stored transposed, vt[dim][token], so that it is the K-major B operand
+            // of P.V in the attention kernel
+            __nv_bfloat16* dst = p.vt + (size_t)(col - 2 * kHid) * p.vt_ld + grow;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              dst[(size_t)j * p.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
+          } else {
+            const float sc = (EPI == kEpiQKV && col < kHid) ? p.qscale : 1.0f;
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(v[2 * j]) + bs[2 * j];
+              float b = __uint_as_float(v[2 * j + 1]) + bs[2 * j + 1];
+              if constexpr (EPI == kEpiGelu) {
+                a = gelu_erf(a);
+                b = gelu_erf(b);
+              } else {
+                a *= sc;
+                b *= sc;
+              }
+              o[j] = pack_bf16x2(a, b);
+            }
+            const int ld = EPI == kEpiQKV ? 2 * kHid : p.N;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)grow * ld + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
+      } else {
+        // bias + residual, row statistics; the pre-LayerNorm value goes back to TMEM (fp32)
+        float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < C::kColsPerThread / 32; ++c) {
+          const int col = (int)half * C::kColsPerThread + c * 32;
+          tmem_ld_32x32(taddr + c * 32, v);
+          uint4 r[4];
+          if (live) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)grow * kHid + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = rp[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld_wait();
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(r);
+          const float* bs = sbias + col;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(v[2 * j]) + bs[2 * j] + bf16_lo(rw[j]);
+            const float b = __uint_as_float(v[2 * j + 1]) + bs[2 * j + 1] + bf16_hi(rw[j]);
+            sum += a + b;
+            sq += a * a + b * b;
+            v[2 * j] = __float_as_uint(a);
+            v[2 * j + 1] = __float_as_uint(b);
+          }
+          tmem_st_32x32(taddr + c * 32, v);
+        }
+        tmem_st_wait();
+        float2* st = sstat + (lt & 1) * 256;
+        st[half * 128 + row] = make_float2(sum, sq);
+        named_bar_sync(1, kGemmEpiThreads);
+        const float2 other = st[(half ^ 1) * 128 + row];
+        const float mean = (sum + other.x) * (1.0f / kHid);
+        const float var = fmaxf((sq + other.y) * (1.0f / kHid) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+#pragma unroll 1
+        for (int c = 0; c < C::kColsPerThread / 32; ++c) {
+          const int col = (int)half * C::kColsPerThread + c * 32;
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (!live) continue;
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * sgamma[col + 2 * j] + sbeta[col + 2 * j];
+            const float b =
+                (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
+            o[j] = pack_bf16x2(a, b);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)grow * kHid + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// varlen attention over packed sequences, one (128-query block, head pair) per work item
+// ---------------------------------------------------------------------------------------------
+// Q and K of a head pair are 64 contiguous bf16 of a qk row = one 128-byte SWIZZLE_128B row; a head
+// is selected by starting the MMA's K slices 64 bytes into the row.  V is read from its transposed
+// copy vt[dim][token] so that keys are the K dimension of P.V.
+constexpr int kAttnSoftmaxWarps = 8;  // 4 per head of the pair
+constexpr int kAttnThreads = 64 + 32 * kAttnSoftmaxWarps;
+constexpr int kKB = 128;              // keys per block
+constexpr int kKVStages = 3;
+constexpr int kQBytes = kBM * 128;            // 128 queries x 64 dims
+constexpr int kKBytes = kKB * 128;            // 128 keys x 64 dims
+constexpr int kVSlab = 64 * 128;              // 64 dims x 64 keys
+constexpr int kVBytes = 2 * kVSlab;           // 128 keys
+constexpr int kKVBytes = kKBytes + kVBytes;
+constexpr int kPSlab = kBM * 128;             // 128 queries x 64 keys
+constexpr int kPBytes = 2 * kPSlab;           // per head
+
+struct AttnSmem {
+  static constexpr int q = 0;                                  // [2]
+  static constexpr int kv = q + 2 * kQBytes;                   // [kKVStages] K | Vt slab 0 | Vt slab 1
+  static constexpr int pp = kv + kKVStages * kKVBytes;         // [2 heads]
+  static constexpr int bars = pp + 2 * kPBytes;
+  static constexpr int nbars = 2 + 2 + 2 * kKVStages + 8;
+  static constexpr int holder = bars + nbars * 8;
+  static constexpr int total = holder + 16;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
+                 const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(sm + AttnSmem::bars);
+  uint64_t* q_empty = q_full + 2;
+  uint64_t* kv_full = q_empty + 2;
+  uint64_t* kv_empty = kv_full + kKVStages;
+  uint64_t* s_full = kv_empty + kKVStages;  // [2 heads]
+  uint64_t* s_free = s_full + 2;
+  uint64_t* p_full = s_free + 2;
+  uint64_t* o_full = p_full + 2;
+  uint32_t* holder = reinterpret_cast<uint32_t*>(sm + AttnSmem::holder);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int n_items = p.nqb * kHeadPairs;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);  // one arrive per softmax warp of the head
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < kKVStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  // TMEM columns: S of head h at [128h, 128h+128), O block of head h at [256+32h, +32)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_qk);
+      tma_prefetch_desc(&tmap_vt);
+      uint32_t li = 0, g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        const QBlock qb = p.qblk[item / kHeadPairs];
+        const int hp = item % kHeadPairs;
+        const uint32_t qbuf = li & 1;
+        mbar_wait(&q_empty[qbuf], ((li >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qbuf], kQBytes);
+        tma_load_2d(sm + AttnSmem::q + qbuf * kQBytes, &tmap_qk, &q_full[qbuf], hp * 64, qb.q_tok0, kEvictNormal);
+        const int nkb = (qb.seq_len + kKB - 1) / kKB;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t stage = g % kKVStages;
+          mbar_wait(&kv_empty[stage], ((g / kKVStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[stage], kKVBytes);
+          uint8_t* dst = sm + AttnSmem::kv + (size_t)stage * kKVBytes;
+          const int tok = qb.seq_tok0 + kb * kKB;
+          tma_load_2d(dst, &tmap_qk, &kv_full[stage], kHid + hp * 64, tok, kEvictNormal);
+          tma_load_2d(dst + kKBytes, &tmap_vt, &kv_full[stage], tok, hp * 64, kEvictNormal);
+          tma_load_2d(dst + kKBytes + kVSlab, &tmap_vt, &kv_full[stage], tok + 64, hp * 64, kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(1u, kBM, kKB);        // S = Q K^T : 128 x 128
+      constexpr uint32_t idesc_o = make_idesc(1u, kBM, kHeadDim);   // O = P V   : 128 x 32
+      uint32_t li = 0, g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        const QBlock qb = p.qblk[item / kHeadPairs];
+        const uint32_t qbuf = li & 1;
+        mbar_wait(&q_full[qbuf], (li >> 1) & 1);
+        const uint32_t q_addr = smem_u32(sm + AttnSmem::q + qbuf * kQBytes);
+        const int nkb = (qb.seq_len + kKB - 1) / kKB;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t stage = g % kKVStages;
+          mbar_wait(&kv_full[stage], (g / kKVStages) & 1);
+          const uint32_t k_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes);
+          const uint32_t v_addr = k_addr + kKBytes;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&s_free[h], (g & 1) ^ 1);  // softmax warps have read the previous S of this head
+            tc_fence_after();
+            const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
+            const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
+            tc_mma<false>(tmem_base + 128 * h, da, db, idesc_s, 0u);
+            tc_mma<false>(tmem_base + 128 * h, da + 2, db + 2, idesc_s, 1u);
+            tc_commit(&s_full[h]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&p_full[h], g & 1);  // P of this block is in shared memory, previous O block was read
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(sm + AttnSmem::pp + h * kPBytes);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              const uint64_t da = make_desc_sw128(p_addr + s * kPSlab);
+              const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma<false>(tmem_base + 256 + 32 * h, da + 2 * kk, db + 2 * kk, idesc_o, (uint32_t)((s | kk) != 0));
+            }
+            tc_commit(&o_full[h]);
+          }
+          tc_commit(&kv_empty[stage]);
+        }
+        tc_commit(&q_empty[qbuf]);
+      }
+    }
+  } else {
+    // ===================== softmax + output =====================
+    const uint32_t quarter = warp & 3;
+    const uint32_t h = (warp - 2) >> 2;
+    const uint32_t row = quarter * 32 + lane;
+    const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + 128 * h;
+    const uint32_t t_o = tmem_base + ((quarter * 32u) << 16) + 256 + 32 * h;
+    uint8_t* prow = sm + AttnSmem::pp + h * kPBytes + row * 128;
+    const uint32_t sw = row & 7;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const QBlock qb = p.qblk[item / kHeadPairs];
+      const int hp = item % kHeadPairs;
+      const int nkb = (qb.seq_len + kKB - 1) / kKB;
+      float m = -INFINITY, l = 0.f;
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = 0.f;
+      uint32_t v[32];
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int valid = qb.seq_len - kb * kKB;  // keys of this block inside the sequence (>= 1)
+        mbar_wait(&s_full[h], g & 1);
+        tc_fence_after();
+        // pass 1: block maximum (scores are already in the log2 domain: q was scaled by log2e/sqrt(32))
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32(t_s + c * 32, v);
+          tmem_ld_wait();
+          if (valid >= (c + 1) * 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        }
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2_approx(m - m_new);  // 0 on the first block (m = -inf)
+        if (kb > 0) {
+          // previous P.V finished: its O block is ready and P may be overwritten
+          mbar_wait(&o_full[h], (g - 1) & 1);
+          tc_fence_after();
+          tmem_ld_32x32(t_o, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = (o[j] + __uint_as_float(v[j])) * alpha;
+          l *= alpha;
+        }
+        m = m_new;
+        // pass 2: p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32(t_s + c * 32, v);
+          tmem_ld_wait();
+          if (c == 3) {
+            // last read of S: the MMA warp may overwrite it with the next block's scores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[h]);
+          }
+          uint32_t pk[16];
+          float ps = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = ex2_approx(__uint_as_float(v[2 * j]) - m);
+            float b = ex2_approx(__uint_as_float(v[2 * j + 1]) - m);
+            if (c * 32 + 2 * j >= valid) a = 0.f;
+            if (c * 32 + 2 * j + 1 >= valid) b = 0.f;
+            pk[j] = pack_bf16x2(a, b);
+            ps += bf16_lo(pk[j]) + bf16_hi(pk[j]);
+          }
+          l += ps;
+          uint8_t* slab = prow + (c >> 1) * kPSlab;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = ((uint32_t)((c & 1) * 4 + j)) ^ sw;
+            *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[h]);
+      }
+      // last O block, normalise, write the context rows of this head
+      mbar_wait(&o_full[h], (g - 1) & 1);
+      tc_fence_after();
+      tmem_ld_32x32(t_o, v);
+      tmem_ld_wait();
+      const int qi = qb.q_tok0 - qb.seq_tok0 + (int)row;  // position of this query in its sequence
+      if (qi < qb.seq_len) {
+        const float inv = 1.0f / l;
+        uint32_t ok[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          ok[j] = pack_bf16x2((o[2 * j] + __uint_as_float(v[2 * j])) * inv,
+                              (o[2 * j + 1] + __uint_as_float(v[2 * j + 1])) * inv);
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + (size_t)(qb.q_tok0 + row) * kHid + (hp * 2 + h) * kHeadDim);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ok[4 * j], ok[4 * j + 1], ok[4 * j + 2], ok[4 * j + 3]);
+      }
+      // the O block of this item has been read: the next item's first P.V may overwrite it only after
+      // this warp arrives on p_full again, which happens after this point (program order)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling + L2 normalisation (sentence-transformers Pooling + Normalize), cross-encoder head
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, int n_seqs, int pool_mode,
+                      float* __restrict__ out) {
+  __shared__ float red[4];
+  const int s = blockIdx.x;
+  if (s >= n_seqs) return;
+  const int t0 = cu[s], t1 = cu[s + 1];
+  float v[3] = {0.f, 0.f, 0.f};
+  if (pool_mode == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = __bfloat162float(x[(size_t)t0 * kHid + threadIdx.x + 128 * i]);
+  } else {
+    for (int t = t0; t < t1; ++t) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] += __bfloat162float(x[(size_t)t * kHid + threadIdx.x + 128 * i]);
+    }
+    const float inv = 1.0f / (float)max(t1 - t0, 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] *= inv;
+  }
+  float sq = warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  const float nrm = sqrtf((red[0] + red[1]) + (red[2] + red[3]));
+  const float inv = 1.0f / fmaxf(nrm, 1e-12f);  // F.normalize(p=2, dim=1, eps=1e-12)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out[(size_t)s * kHid + threadIdx.x + 128 * i] = v[i] * inv;
+}
+
+__global__ void __launch_bounds__(384)
+ce_head_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, int n_seqs,
+               const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ wc,
+               const float* __restrict__ bc, float* __restrict__ logits) {
+  __shared__ float xs[kHid];
+  __shared__ float pooled[kHid];
+  __shared__ float red[12];
+  const int s = blockIdx.x;
+  if (s >= n_seqs) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  xs[threadIdx.x] = __bfloat162float(x[(size_t)cu[s] * kHid + threadIdx.x]);
+  __syncthreads();
+  for (int o = warp * 32; o < warp * 32 + 32; ++o) {
+    const float* w = wp + (size_t)o * kHid;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a = fmaf(__ldg(w + lane + 32 * i), xs[lane + 32 * i], a);
+    a = warp_sum(a);
+    if (lane == 0) pooled[o] = tanhf(a + bp[o]);
+  }
+  __syncthreads();
+  float a = warp_sum(pooled[threadIdx.x] * wc[threadIdx.x]);
+  if (lane == 0) red[warp] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 12; ++i) t += red[i];
+    logits[s] = t + bc[0];
+  }
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t n, float* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+size_t gemm_smem_bytes(int epi) {
+  return (epi == kEpiResLN ? GemmCfg<384>::kTotal : GemmCfg<192>::kTotal) + 1024;
+}
+size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
+
+cudaError_t launch_positions(const int32_t* cu_seqlens, int n_seqs, int32_t* pos_ids, cudaStream_t st) {
+  if (n_seqs <= 0) return cudaSuccess;
+  positions_kernel<<<n_seqs, 128, 0, st>>>(cu_seqlens, n_seqs, pos_ids);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* pos_ids, int M,
+                            int vocab, const float* word, const float* pos, const float* type,
+                            const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
+                            cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  embed_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, type_ids, pos_ids, M, vocab, word, pos, type, gamma, beta, eps, x);
+  return cudaGetLastError();
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                                 cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = GemmCfg<BN>::kTotal + 1024;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (p.N % BN != 0 || p.K % 64 != 0 || p.N > 1536) return cudaErrorInvalidValue;
+  const int tiles = p.num_mtiles * (p.N / BN);
+  if (tiles <= 0) return cudaSuccess;
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
+                        const GemmParams& p, cudaStream_t st) {
+  switch (epi) {
+    case kEpiQKV: return launch_gemm_t<192, kEpiQKV>(sm_count, tmap_a, tmap_b, p, st);
+    case kEpiGelu: return launch_gemm_t<192, kEpiGelu>(sm_count, tmap_a, tmap_b, p, st);
+    case kEpiResLN: return launch_gemm_t<384, kEpiResLN>(sm_count, tmap_a, tmap_b, p, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_vt,
+                             const AttnParams& p, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = attn_smem_bytes();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int items = p.nqb * kHeadPairs;
+  if (items <= 0) return cudaSuccess;
+  const int grid = items < sm_count ? items : sm_count;
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs,
+                                  int pool_mode, float* out, cudaStream_t st) {
+  if (n_seqs <= 0) return cudaSuccess;
+  pool_normalize_kernel<<<n_seqs, 128, 0, st>>>(x, cu_seqlens, n_seqs, pool_mode, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs, const float* wp,
+                           const float* bp, const float* wc, const float* bc, float* logits,
+                           cudaStream_t st) {
+  if (n_seqs <= 0) return cudaSuccess;
+  ce_head_kernel<<<n_seqs, 384, 0, st>>>(x, cu_seqlens, n_seqs, wp, bp, wc, bc, logits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bf16_to_f32(const __nv_bfloat16* src, int64_t n, float* dst, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  bf16_to_f32_kernel<<<grid, 256, 0, st>>>(src, n, dst);
+  return cudaGetLastError();
+}
+cudaError_t launch_f32_to_bf16(const float* src, int64_t n, __nv_bfloat16* dst, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  f32_to_bf16_kernel<<<grid, 256, 0, st>>>(src, n, dst);
+  return cudaGetLastError();
+}
+
+}  // namespace frs

@@ -1,0 +1,89 @@
+// bert.cuh — launch interface of the BERT encoder kernels (kernels in bert.cu).
+//
+// These replace the torch/ATen ops that SentenceTransformer.encode (reference main.py:148,213,
+// main2.py:171) and CrossEncoder.predict (main.py:245, main2.py:166) execute through
+// transformers' BertModel (modeling_bert.py): embeddings+LayerNorm (:102-112), self-attention
+// (:115-207), output projections with residual+LayerNorm (:294-298, :352-356), erf-GELU FFN
+// (:339-342), CLS/mean pooling + L2 normalisation, and the pooler+classifier head (:462-468,
+// :1111-1124).  Tokens of a batch are PACKED (no padding): sequence s owns rows
+// [cu_seqlens[s], cu_seqlens[s+1]) of every activation matrix.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace frs {
+
+constexpr int kHid = 384;        // hidden size of both checkpoints
+constexpr int kHeads = 12;
+constexpr int kHeadDim = 32;
+constexpr int kHeadPairs = kHeads / 2;  // attention works on pairs of heads: 64 dims = one 128-byte row
+constexpr int kFfn = 1536;
+constexpr int kQkvN = 3 * kHid;  // fused q|k|v projection
+constexpr int kBM = 128;         // token rows per GEMM / attention tile == MMA M == TMEM lanes
+constexpr int kMaxSeq = 512;     // max_position_embeddings
+
+enum GemmEpi {
+  kEpiQKV = 0,    // + bias; q scaled by log2(e)/sqrt(32); q|k -> qk[M,768] bf16, v -> vt[384,M] bf16 (transposed)
+  kEpiGelu = 1,   // gelu(acc + bias) -> bf16 [M, N]
+  kEpiResLN = 2,  // LayerNorm(acc + bias + residual) * gamma + beta -> bf16 [M, 384]
+};
+
+struct GemmParams {
+  int M;           // live token rows
+  int num_mtiles;  // ceil(M / 128)
+  int N, K;
+  const float* bias;   // [N]
+  __nv_bfloat16* out;  // QKV: qk [rows, 768]; GELU: [rows, N]; ResLN: [rows, 384]
+  __nv_bfloat16* vt;   // QKV only: [384, vt_ld]
+  int64_t vt_ld;
+  float qscale;
+  const __nv_bfloat16* resid;  // ResLN only: [rows, 384]
+  const float* gamma;
+  const float* beta;
+  float eps;
+};
+
+// one entry per (sequence, 128-query block)
+struct QBlock {
+  int32_t q_tok0;    // first token row of this query block
+  int32_t seq_tok0;  // first token row of the sequence
+  int32_t seq_len;
+  int32_t pad;
+};
+
+struct AttnParams {
+  const QBlock* qblk;
+  int nqb;             // work items = nqb * kHeadPairs
+  __nv_bfloat16* ctx;  // [rows, 384]
+};
+
+size_t gemm_smem_bytes(int epi);
+size_t attn_smem_bytes();
+
+// pos_ids[t] = t - seq_tok0 for every packed token (one block per sequence)
+cudaError_t launch_positions(const int32_t* cu_seqlens, int n_seqs, int32_t* pos_ids, cudaStream_t st);
+// x = LayerNorm(word[id] + pos[p] + type[tt]) -> bf16 ; type_ids may be null (all 0)
+cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* pos_ids, int M,
+                            int vocab, const float* word, const float* pos, const float* type,
+                            const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
+                            cudaStream_t st);
+// C = A[M,K] * W[N,K]^T (+ epilogue).  tmap_a: activations, box 64 x 128, SWIZZLE_128B;
+// tmap_b: weights, box 64 x 192, SWIZZLE_128B.
+cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
+                        const GemmParams& p, cudaStream_t st);
+// tmap_qk: qk [rows, 768], box 64 x 128; tmap_vt: vt [384, rows], box 64 x 64; both SWIZZLE_128B
+cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_vt,
+                             const AttnParams& p, cudaStream_t st);
+// pool_mode 0 = CLS row, 1 = mean over the sequence; then x / max(||x||, 1e-12)
+cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs,
+                                  int pool_mode, float* out, cudaStream_t st);
+// logits[s] = wc . tanh(Wp * x[cls_s] + bp) + bc
+cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs, const float* wp,
+                           const float* bp, const float* wc, const float* bc, float* logits,
+                           cudaStream_t st);
+cudaError_t launch_bf16_to_f32(const __nv_bfloat16* src, int64_t n, float* dst, cudaStream_t st);
+cudaError_t launch_f32_to_bf16(const float* src, int64_t n, __nv_bfloat16* dst, cudaStream_t st);
+
+}  // namespace frs

@@ -36,6 +36,16 @@ static int set_err(int code, const char* fmt, ...) {
                      __FILE__, __LINE__);                                                     \
   } while (0)
 
+namespace frs {
+int abi_set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace frs
+
 extern "C" const char* frs_last_error(void) { return g_err; }
 extern "C" int frs_version(void) { return FRS_VERSION; }
 extern "C" int frs_device_count(void) {
@@ -66,6 +76,25 @@ static int get_encode_fn(EncodeTiledFn* out) {
   *out = fn;
   return FRS_OK;
 }
+
+namespace frs {
+// generic 2-D bf16 row-major [rows, cols] map with a (box_cols x box_rows) SWIZZLE_128B box
+int abi_make_tmap_bf16(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                       uint32_t box_rows) {
+  EncodeTiledFn enc = nullptr;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(FRS_E_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+  return FRS_OK;
+}
+}  // namespace frs
 
 // [rows, 384] row-major matrix, box = one 128-byte-wide K-slab of `box_rows` rows, SWIZZLE_128B
 static int make_tmap(CUtensorMap* m, void* base, bool f32, uint64_t rows, uint32_t box_rows) {

@@ -162,7 +162,9 @@ int frs_index_read_timeline(frs_index* idx, uint64_t* host_out, int n_ctas);
 
 /* ---- encoders: replace SentenceTransformer.encode / CrossEncoder.predict -
  * BertModel forward (transformers/models/bert/modeling_bert.py) for the two
- * checkpoints of main.py:84,90.  Declared here; see encoder section of DESIGN.md. */
+ * checkpoints of main.py:84,90 (get_embedder / get_reranker).  Tokenisation
+ * (WordPiece) stays on the host; the library takes PACKED token ids: sequence s
+ * owns ids[cu_seqlens[s] .. cu_seqlens[s+1]), no padding anywhere. */
 typedef struct frs_bert_cfg {
   int32_t vocab_size;    /* 30522 */
   int32_t hidden;        /* 384   */
@@ -174,6 +176,61 @@ typedef struct frs_bert_cfg {
   int32_t has_head;      /* 1 = pooler + 1-logit classifier (cross-encoder) */
   float ln_eps;          /* 1e-12 */
 } frs_bert_cfg;
+
+#define FRS_MAX_LAYERS 12
+#define FRS_MAX_SEQ 512 /* max_position_embeddings; SentenceTransformer / CrossEncoder truncate here */
+#define FRS_POOL_CLS 0  /* bge-small-en-v1.5: pooling_mode_cls_token */
+#define FRS_POOL_MEAN 1 /* masked mean (all-MiniLM-L6-v2 of evaluate.py:22) */
+
+/* Weight table of frs_encoder_create: fp32 tensors in HF state_dict layout ([out, in] Linear
+ * weights), in this order (n = 5 + 16 * layers + 4 * has_head):
+ *   0 embeddings.word_embeddings [vocab,384]   1 position_embeddings [512,384]
+ *   2 token_type_embeddings [2,384]            3,4 embeddings.LayerNorm weight, bias
+ *   per layer l, base 5 + 16 l:
+ *     +0,+1 attention.self.query w,b    +2,+3 key w,b      +4,+5 value w,b
+ *     +6,+7 attention.output.dense w,b  +8,+9 attention.output.LayerNorm w,b
+ *     +10,+11 intermediate.dense w [1536,384], b           +12,+13 output.dense w [384,1536], b
+ *     +14,+15 output.LayerNorm w,b
+ *   head: pooler.dense w,b ; classifier w [1,384], b [1]
+ * GEMM weights are converted to bf16 once at creation; biases / LayerNorm / embeddings stay fp32. */
+#define FRS_BERT_WEIGHTS(layers, has_head) (5 + 16 * (layers) + ((has_head) ? 4 : 0))
+
+/* weights: array of n_weights pointers (host memory if !on_device, else device memory of `device`).
+ * max_tokens: packed tokens one forward pass can hold (workspace is ~7.7 KB per token). */
+int frs_encoder_create(int device, const frs_bert_cfg* cfg, const float* const* weights, int n_weights,
+                       int on_device, int max_tokens, frs_encoder** out);
+int frs_encoder_destroy(frs_encoder* enc);
+int frs_encoder_max_tokens(const frs_encoder* enc);
+
+/* SentenceTransformer.encode(texts)  main.py:148,213 main2.py:171 — BERT forward, pooling, L2 normalise.
+ *   dev_ids          [total] int32 packed WordPiece ids ([CLS] ... [SEP] per sequence)
+ *   host_cu_seqlens  [n_seqs+1] int32 prefix sums (HOST memory), every length in [1, FRS_MAX_SEQ]
+ *   dev_out          [n_seqs, 384] fp32, rows L2-normalised
+ * The device-pointer form needs total <= max_tokens; the *_host form takes host buffers of any
+ * size and runs as many passes as needed. */
+int frs_encoder_embed(frs_encoder* enc, const int32_t* dev_ids, const int32_t* host_cu_seqlens, int n_seqs,
+                      int pool_mode, float* dev_out, void* stream);
+int frs_encoder_embed_host(frs_encoder* enc, const int32_t* host_ids, const int32_t* host_cu_seqlens,
+                           int n_seqs, int pool_mode, float* host_out);
+/* CrossEncoder.predict(pairs)  main.py:245 main2.py:166 — [CLS] q [SEP] d [SEP] with token types 0/1,
+ * BERT forward, pooler (tanh) and the 1-logit classifier; raw logits (no activation). */
+int frs_encoder_score_pairs(frs_encoder* enc, const int32_t* dev_ids, const int32_t* dev_type_ids,
+                            const int32_t* host_cu_seqlens, int n_seqs, float* dev_logits, void* stream);
+int frs_encoder_score_pairs_host(frs_encoder* enc, const int32_t* host_ids, const int32_t* host_type_ids,
+                                 const int32_t* host_cu_seqlens, int n_seqs, float* host_logits);
+/* last_hidden_state of the most recent forward pass, widened to fp32: [n_tokens, 384] (test aid) */
+int frs_encoder_last_hidden(frs_encoder* enc, float* dev_out, int n_tokens, void* stream);
+/* diagnostics: the first n_elems bf16 values of a workspace buffer of the most recent pass, widened
+ * to fp32.  which: 0 x0 [T,384] (layer output), 1 x1 [T,384] (after attention block), 2 qk [T,768]
+ * (scaled q | k), 3 vt [384,T] (v transposed, T = max_tokens), 4 ctx [T,384], 5 h [T,1536].
+ * With a 1-layer model this exposes every stage of a layer.  Test aid, not a product path. */
+int frs_encoder_debug_read(frs_encoder* enc, int which, float* dev_out, int64_t n_elems, void* stream);
+/* Profiling (off by default): CUDA events around every kernel of a forward pass.  read_profile
+ * synchronises and returns the milliseconds of the LAST pass per kernel class:
+ * [0] embeddings+LN, [1] QKV GEMM, [2] attention, [3] out-proj GEMM+LN, [4] FFN-up GEMM+GELU,
+ * [5] FFN-down GEMM+LN, [6] pooling / head, [7] kernels launched */
+int frs_encoder_set_profiling(frs_encoder* enc, int on);
+int frs_encoder_read_profile(frs_encoder* enc, double* host_out8);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,264 @@
+"""Parity of the CUDA encoders (through the C ABI) with the oracle (oracle/encoder_oracle.py, pinned to
+transformers' BertModel in tests/test_encoder_oracle_cpu.py).
+
+Arithmetic: bf16 operands and activations, fp32 accumulation / LayerNorm / softmax statistics.
+Tolerances (north_star: "1e-2 absolute for bf16"):
+    embedding components (unit-norm rows, |x| ~ 0.05)   <= 1e-2 absolute  (measured ~1e-3)
+    cosine(ours, oracle) per text                        >= 0.999
+    reranker logits                                       <= 5e-2 absolute and <= 1e-2 on average
+                                                          (12 bf16 roundings per layer, |logit| up to ~4)
+    per-stage activations of one layer                    <= 0.05 absolute on O(1) values
+"""
+import numpy as np
+import pytest
+import torch
+
+from financial_rag_system_b200.checkpoint import BGE_SMALL, MINILM_L6_CE, BertShape, synthetic_checkpoint
+from financial_rag_system_b200.tokenizer import CLS, SEP
+
+pytestmark = pytest.mark.gpu
+
+LOG2E = 1.4426950408889634
+
+
+def _random_batch(lens, seed, vocab=30522, pairs=False):
+    rng = np.random.default_rng(seed)
+    cu = np.zeros(len(lens) + 1, dtype=np.int32)
+    np.cumsum(lens, out=cu[1:])
+    ids = rng.integers(1000, vocab, size=int(cu[-1])).astype(np.int32)
+    tts = np.zeros_like(ids)
+    for i, n in enumerate(lens):
+        ids[cu[i]] = CLS
+        if n > 1:
+            ids[cu[i + 1] - 1] = SEP
+        if pairs and n > 4:
+            cut = cu[i] + max(2, n // 5)
+            ids[cut] = SEP
+            tts[cut + 1:cu[i + 1]] = 1
+    return ids, tts, cu
+
+
+@pytest.fixture(scope="module")
+def bge():
+    from financial_rag_system_b200.encoder import BertEncoder
+
+    w = synthetic_checkpoint(BGE_SMALL, 1234)
+    enc = BertEncoder(BGE_SMALL, w, device=0, max_tokens=8192)
+    yield enc, w
+    enc.close()
+
+
+@pytest.fixture(scope="module")
+def ce():
+    from financial_rag_system_b200.encoder import BertEncoder
+
+    w = synthetic_checkpoint(MINILM_L6_CE, 4321)
+    enc = BertEncoder(MINILM_L6_CE, w, device=0, max_tokens=8192)
+    yield enc, w
+    enc.close()
+
+
+def test_every_stage_of_one_layer_matches_the_oracle():
+    """1-layer model: the workspace after the pass holds every intermediate of the layer."""
+    import torch.nn.functional as F
+
+    from financial_rag_system_b200.encoder import BertEncoder
+    from oracle import encoder_oracle as eo
+
+    shape = BertShape(layers=1)
+    w = synthetic_checkpoint(shape, 77)
+    enc = BertEncoder(shape, w, device=0, max_tokens=2048)
+    lens = [5, 128, 129, 300, 512, 1, 77, 256]
+    ids, _, cu = _random_batch(lens, 5)
+    M = int(cu[-1])
+    enc.embed_packed(ids, cu)
+    T = enc.max_tokens
+    got = {
+        "qk": enc.debug_read(2, M * 768).cpu().numpy().reshape(M, 768),
+        "vt": enc.debug_read(3, 384 * T).cpu().numpy().reshape(384, T)[:, :M].T,
+        "ctx": enc.debug_read(4, M * 384).cpu().numpy().reshape(M, 384),
+        "x1": enc.debug_read(1, M * 384).cpu().numpy().reshape(M, 384),
+        "h": enc.debug_read(5, M * 1536).cpu().numpy().reshape(M, 1536),
+        "x0": enc.debug_read(0, M * 384).cpu().numpy().reshape(M, 384),
+    }
+    enc.close()
+
+    # oracle stages, sequence by sequence (no padding involved)
+    t = lambda n: torch.from_numpy(w[n])
+    pre = "encoder.layer.0."
+    ref = {k: [] for k in got}
+    with torch.no_grad():
+        for i in range(len(lens)):
+            sl = slice(cu[i], cu[i + 1])
+            pid = torch.from_numpy(ids[sl].astype(np.int64))[None]
+            x = eo.bert_embeddings(w, pid, torch.zeros_like(pid), shape.ln_eps)
+            q = F.linear(x, t(pre + "attention.self.query.weight"), t(pre + "attention.self.query.bias"))
+            k = F.linear(x, t(pre + "attention.self.key.weight"), t(pre + "attention.self.key.bias"))
+            v = F.linear(x, t(pre + "attention.self.value.weight"), t(pre + "attention.self.value.bias"))
+            ref["qk"].append(torch.cat([q * (LOG2E / np.sqrt(32.0)), k], -1)[0].numpy())
+            ref["vt"].append(v[0].numpy())
+            mask = torch.ones((1, pid.shape[1]))
+            ctx = eo.bert_self_attention(w, pre, x, mask)
+            ref["ctx"].append(ctx[0].numpy())
+            a = F.linear(ctx, t(pre + "attention.output.dense.weight"), t(pre + "attention.output.dense.bias"))
+            x1 = F.layer_norm(a + x, (384,), t(pre + "attention.output.LayerNorm.weight"),
+                              t(pre + "attention.output.LayerNorm.bias"), shape.ln_eps)
+            ref["x1"].append(x1[0].numpy())
+            h = F.gelu(F.linear(x1, t(pre + "intermediate.dense.weight"), t(pre + "intermediate.dense.bias")))
+            ref["h"].append(h[0].numpy())
+            ref["x0"].append(eo.bert_layer(w, 0, x, mask, shape.ln_eps)[0].numpy())
+    for name in ("qk", "vt", "ctx", "x1", "h", "x0"):
+        r = np.concatenate(ref[name], 0)
+        err = np.abs(got[name] - r)
+        print(f"{name}: max|ref| {np.abs(r).max():.3f}  max err {err.max():.4f}  mean err {err.mean():.5f}")
+        assert np.isfinite(got[name]).all(), name
+        assert err.max() <= 0.05 + 0.01 * np.abs(r).max(), f"{name}: max err {err.max()}"
+        assert err.mean() <= 0.006, f"{name}: mean err {err.mean()}"
+
+
+def test_embed_matches_oracle_cls_and_mean(bge):
+    from oracle import encoder_oracle as eo
+
+    enc, w = bge
+    lens = [16, 9, 230, 512, 1, 2, 127, 128, 129, 384, 33, 257]
+    ids, _, cu = _random_batch(lens, 11)
+    for pool, name in ((0, "cls"), (1, "mean")):
+        got = enc.embed_packed(ids, cu, pool)
+        ref = eo.embed(BGE_SMALL, w, ids, cu, name)
+        err = np.abs(got - ref)
+        cos = (got * ref).sum(1)
+        print(f"{name}: max err {err.max():.5f} mean {err.mean():.6f} min cos {cos.min():.6f}")
+        assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+        assert err.max() <= 1e-2, err.max()
+        assert cos.min() >= 0.999, cos.min()
+
+
+def test_last_hidden_state_matches_oracle(bge):
+    from oracle import encoder_oracle as eo
+
+    enc, w = bge
+    lens = [40, 300, 7]
+    ids, _, cu = _random_batch(lens, 3)
+    enc.embed_packed(ids, cu)
+    got = enc.last_hidden(int(cu[-1])).cpu().numpy()
+    ref = eo.last_hidden_packed(BGE_SMALL, w, ids, cu)
+    err = np.abs(got - ref)
+    print(f"last hidden: max|ref| {np.abs(ref).max():.2f} max err {err.max():.4f} mean err {err.mean():.5f}")
+    assert err.mean() <= 0.02 and err.max() <= 0.25
+
+
+def test_reranker_logits_match_oracle(ce):
+    from oracle import encoder_oracle as eo
+
+    enc, w = ce
+    rng = np.random.default_rng(2)
+    lens = [int(x) for x in rng.integers(20, 513, size=15)] + [512, 4]
+    ids, tts, cu = _random_batch(lens, 21, pairs=True)
+    got = enc.score_packed(ids, tts, cu)
+    ref = eo.score_pairs(MINILM_L6_CE, w, ids, tts, cu)
+    err = np.abs(got - ref)
+    print(f"logits: range [{ref.min():.2f}, {ref.max():.2f}] max err {err.max():.4f} mean err {err.mean():.4f}")
+    assert err.max() <= 5e-2 and err.mean() <= 1e-2
+    # rerank_documents (main.py:246): the order the reference derives from the logits
+    top = eo.rerank(ref[:15], 5)
+    gap = np.sort(ref[:15])[::-1]
+    if np.min(gap[:5] - gap[1:6]) > 0.1:
+        assert np.array_equal(eo.rerank(got[:15], 5), top)
+
+
+def test_token_types_matter(ce):
+    enc, _ = ce
+    ids, tts, cu = _random_batch([64, 200], 8, pairs=True)
+    a = enc.score_packed(ids, tts, cu)
+    b = enc.score_packed(ids, np.zeros_like(tts), cu)
+    assert np.abs(a - b).max() > 1e-3
+
+
+def test_result_is_independent_of_batch_composition_and_order(bge):
+    """A text's embedding must not depend on what else is in the batch, on its position in it, or
+    on how the batch is split into passes — bit for bit."""
+    enc, _ = bge
+    lens = [16, 230, 512, 3, 129, 64]
+    ids, _, cu = _random_batch(lens, 17)
+    full = enc.embed_packed(ids, cu)
+    again = enc.embed_packed(ids, cu)
+    assert np.array_equal(full, again), "not deterministic"
+    for i in (0, 2, 4):
+        one = enc.embed_packed(ids[cu[i]:cu[i + 1]], np.array([0, lens[i]], dtype=np.int32))
+        assert np.array_equal(one[0], full[i]), f"text {i} changes with its batch"
+    order = [3, 5, 1, 0, 4, 2]
+    pid = np.concatenate([ids[cu[i]:cu[i + 1]] for i in order])
+    pcu = np.concatenate([[0], np.cumsum([lens[i] for i in order])]).astype(np.int32)
+    perm = enc.embed_packed(pid, pcu)
+    assert np.array_equal(perm, full[order])
+
+
+def test_batches_larger_than_the_workspace_run_in_passes():
+    from financial_rag_system_b200.encoder import BertEncoder
+
+    shape = BertShape(layers=2)
+    w = synthetic_checkpoint(shape, 5)
+    small = BertEncoder(shape, w, device=0, max_tokens=640)
+    big = BertEncoder(shape, w, device=0, max_tokens=8192)
+    lens = [300, 200, 512, 100, 90, 400, 17]
+    ids, _, cu = _random_batch(lens, 4)
+    a = small.embed_packed(ids, cu)
+    b = big.embed_packed(ids, cu)
+    small.close()
+    big.close()
+    assert np.array_equal(a, b)
+
+
+def test_bad_sequences_are_rejected(bge):
+    from financial_rag_system_b200 import FrsError
+
+    enc, _ = bge
+    ids = np.full(600, 2000, dtype=np.int32)
+    with pytest.raises(FrsError):
+        enc.embed_packed(ids, np.array([0, 600], dtype=np.int32))  # longer than 512
+    with pytest.raises(FrsError):
+        enc.embed_packed(ids, np.array([0, 10, 10], dtype=np.int32))  # empty sequence
+    with pytest.raises(FrsError):
+        enc.score_packed(ids[:10], np.zeros(10, np.int32), np.array([0, 10], dtype=np.int32))  # no head
+
+
+def test_device_pointer_entry_point_matches_host_entry_point(bge):
+    enc, _ = bge
+    ids, _, cu = _random_batch([50, 400, 12], 6)
+    host = enc.embed_packed(ids, cu)
+    dev = enc.embed_device(torch.from_numpy(ids).cuda(), cu)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_text_surface_embedder_and_reranker_follow_the_reference_contract():
+    """`.encode` / `.predict` as main.py:148,213,245 call them: shapes, dtype, order, str input."""
+    from financial_rag_system_b200.encoder import Embedder, Reranker
+    from financial_rag_system_b200.tokenizer import WordPiece
+    from oracle import encoder_oracle as eo
+
+    tok = WordPiece.synthetic()
+    emb = Embedder(device=0, max_tokens=4096, tokenizer=tok)
+    texts = ["What was Apple's total revenue in fiscal 2023?", "Net sales increased 8% year over year.",
+             "Risk factors include competition and supply chain disruption. " * 12]
+    e = emb.encode(texts)
+    assert e.shape == (3, 384) and e.dtype == np.float32
+    assert emb.encode(texts[0]).shape == (384,)
+    assert np.array_equal(emb.encode(texts[1]), e[1])
+    assert emb.encode([]).shape == (0, 384)
+    assert len(e.tolist()) == 3  # main.py:148 `.tolist()`
+    ids, cu = tok.pack_texts(texts)
+    ref = eo.embed(BGE_SMALL, synthetic_checkpoint(BGE_SMALL, Embedder.SYNTHETIC_SEED), ids, cu)
+    assert np.abs(e - ref).max() <= 1e-2
+    emb.close()
+
+    rr = Reranker(device=0, max_tokens=4096, tokenizer=tok)
+    q = "How did iPhone revenue change?"
+    pairs = [[q, t] for t in texts]
+    s = rr.predict(pairs)
+    assert s.shape == (3,) and s.dtype == np.float32
+    pi, pt, pc = tok.pack_pairs(pairs)
+    ref = eo.score_pairs(MINILM_L6_CE, synthetic_checkpoint(MINILM_L6_CE, Reranker.SYNTHETIC_SEED), pi, pt, pc)
+    assert np.abs(s - ref).max() <= 5e-2
+    assert rr.predict([]).shape == (0,)
+    rr.close()
