@@ -15,11 +15,50 @@
 // SWIZZLE_128B shared-memory slabs; warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM
 // allocation), warps 2..9 epilogue / softmax (a thread owns one token row = one TMEM lane).
 #include <math.h>
+#include <stdlib.h>
 
 #include "bert.cuh"
 #include "common.cuh"
 
 namespace frs {
+
+// ---------------------------------------------------------------------------------------------
+// protocol-bug diagnostics: a barrier wait that times out records WHICH wait it was in mapped host
+// memory (readable after the trap has killed the context) — see frs_debug_trap_info()
+// ---------------------------------------------------------------------------------------------
+__device__ uint32_t* g_trap_info = nullptr;  // [4]: code, blockIdx.x, parity, threadIdx.x
+static uint32_t* g_trap_info_host = nullptr;
+
+__device__ __noinline__ void trap_with_code(uint32_t code, uint32_t parity) {
+  if (g_trap_info) {
+    if (atomicCAS(g_trap_info, 0u, code) == 0u) {
+      g_trap_info[1] = blockIdx.x;
+      g_trap_info[2] = parity;
+      g_trap_info[3] = threadIdx.x;
+      __threadfence_system();
+    }
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_c(uint64_t* bar, uint32_t parity, uint32_t code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) trap_with_code(code, parity);
+  }
+}
+
+uint32_t* bert_trap_info_host() {
+  if (!g_trap_info_host) {
+    uint32_t* h = nullptr;
+    if (cudaHostAlloc(&h, 16, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(h, 0, 16);
+    uint32_t* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return nullptr;
+    if (cudaMemcpyToSymbol(g_trap_info, &d, sizeof(d)) != cudaSuccess) return nullptr;
+    g_trap_info_host = h;
+  }
+  return g_trap_info_host;
+}
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
@@ -185,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
-          mbar_wait(&empty[stage], ph ^ 1);
+          mbar_wait_c(&empty[stage], ph ^ 1, 101u);
           mbar_arrive_expect_tx(&full[stage], C::kStage);
           uint8_t* sa = ring + (size_t)stage * C::kStage;
           tma_load_2d(sa, &tmap_a, &full[stage], ks * 64, mt * kBM, kEvictNormal);
@@ -204,13 +243,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t acc = lt % C::kAcc;
         const uint32_t aph = (lt / C::kAcc) & 1;
-        mbar_wait(&tempty[acc], aph ^ 1);
+        mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
-          mbar_wait(&full[stage], ph);
+          mbar_wait_c(&full[stage], ph, 103u);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + (size_t)stage * C::kStage);
           const uint64_t da = make_desc_sw128(sa);
@@ -238,7 +277,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t aph = (lt / C::kAcc) & 1;
       const int grow = mt * kBM + (int)row;
       const bool live = grow < p.M;
-      mbar_wait(&tfull[acc], aph);
+      mbar_wait_c(&tfull[acc], aph, 104u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN + half * C::kColsPerThread;
       uint32_t v[32];
@@ -428,19 +467,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const QBlock qb = p.qblk[item / kHeadPairs];
         const int hp = item % kHeadPairs;
         const uint32_t qbuf = li & 1;
-        mbar_wait(&q_empty[qbuf], ((li >> 1) & 1) ^ 1);
+        mbar_wait_c(&q_empty[qbuf], ((li >> 1) & 1) ^ 1, 105u);
         mbar_arrive_expect_tx(&q_full[qbuf], kQBytes);
         tma_load_2d(sm + AttnSmem::q + qbuf * kQBytes, &tmap_qk, &q_full[qbuf], hp * 64, qb.q_tok0, kEvictNormal);
-        const int nkb = (qb.seq_len + kKB - 1) / kKB;
+        const int nkb = (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const uint32_t stage = g % kKVStages;
-          mbar_wait(&kv_empty[stage], ((g / kKVStages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&kv_full[stage], kKVBytes);
+          mbar_wait_c(&kv_empty[stage], ((g / kKVStages) & 1) ^ 1, 106u);
+          mbar_arrive_expect_tx(&kv_full[stage], (p.debug & 4) ? kKBytes : kKVBytes);
           uint8_t* dst = sm + AttnSmem::kv + (size_t)stage * kKVBytes;
-          const int tok = qb.seq_tok0 + kb * kKB;
+          const int tok = qb.kv_tok0 + kb * kKB;
           tma_load_2d(dst, &tmap_qk, &kv_full[stage], kHid + hp * 64, tok, kEvictNormal);
-          tma_load_2d(dst + kKBytes, &tmap_vt, &kv_full[stage], tok, hp * 64, kEvictNormal);
-          tma_load_2d(dst + kKBytes + kVSlab, &tmap_vt, &kv_full[stage], tok + 64, hp * 64, kEvictNormal);
+          if (!(p.debug & 4)) {
+            tma_load_2d(dst + kKBytes, &tmap_vt, &kv_full[stage], tok, hp * 64, kEvictNormal);
+            tma_load_2d(dst + kKBytes + kVSlab, &tmap_vt, &kv_full[stage], tok + 64, hp * 64, kEvictNormal);
+          }
         }
       }
     }
@@ -453,33 +494,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
         const QBlock qb = p.qblk[item / kHeadPairs];
         const uint32_t qbuf = li & 1;
-        mbar_wait(&q_full[qbuf], (li >> 1) & 1);
+        mbar_wait_c(&q_full[qbuf], (li >> 1) & 1, 107u);
         const uint32_t q_addr = smem_u32(sm + AttnSmem::q + qbuf * kQBytes);
-        const int nkb = (qb.seq_len + kKB - 1) / kKB;
+        const int nkb = (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const uint32_t stage = g % kKVStages;
-          mbar_wait(&kv_full[stage], (g / kKVStages) & 1);
+          mbar_wait_c(&kv_full[stage], (g / kKVStages) & 1, 108u);
           const uint32_t k_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes);
           const uint32_t v_addr = k_addr + kKBytes;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&s_free[h], (g & 1) ^ 1);  // softmax warps have read the previous S of this head
+            mbar_wait_c(&s_free[h], (g & 1) ^ 1, 109u);  // softmax warps have read the previous S of this head
             tc_fence_after();
             const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
             const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
-            tc_mma<false>(tmem_base + 128 * h, da, db, idesc_s, 0u);
-            tc_mma<false>(tmem_base + 128 * h, da + 2, db + 2, idesc_s, 1u);
+            if (!(p.debug & 2)) {
+              tc_mma<false>(tmem_base + 128 * h, da, db, idesc_s, 0u);
+              tc_mma<false>(tmem_base + 128 * h, da + 2, db + 2, idesc_s, 1u);
+            }
             tc_commit(&s_full[h]);
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&p_full[h], g & 1);  // P of this block is in shared memory, previous O block was read
+            mbar_wait_c(&p_full[h], g & 1, 110u);  // P of this block is in shared memory, previous O block was read
             tc_fence_after();
             const uint32_t p_addr = smem_u32(sm + AttnSmem::pp + h * kPBytes);
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
               const uint64_t da = make_desc_sw128(p_addr + s * kPSlab);
               const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
+              if (p.debug & 1) continue;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 tc_mma<false>(tmem_base + 256 + 32 * h, da + 2 * kk, db + 2 * kk, idesc_o, (uint32_t)((s | kk) != 0));
@@ -504,15 +548,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const QBlock qb = p.qblk[item / kHeadPairs];
       const int hp = item % kHeadPairs;
-      const int nkb = (qb.seq_len + kKB - 1) / kKB;
+      const int key_off = qb.seq_tok0 - qb.kv_tok0;  // keys of the first block before the sequence (< 8)
+      const int nkb = (key_off + qb.seq_len + kKB - 1) / kKB;
       float m = -INFINITY, l = 0.f;
       float o[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[j] = 0.f;
       uint32_t v[32];
       for (int kb = 0; kb < nkb; ++kb, ++g) {
-        const int valid = qb.seq_len - kb * kKB;  // keys of this block inside the sequence (>= 1)
-        mbar_wait(&s_full[h], g & 1);
+        // keys [lo, hi) of this block belong to the sequence (hi - lo >= 1)
+        const int lo = kb == 0 ? key_off : 0;
+        const int hi = min(kKB, key_off + qb.seq_len - kb * kKB);
+        const bool full = lo == 0 && hi == kKB;
+        mbar_wait_c(&s_full[h], g & 1, 111u);
         tc_fence_after();
         // pass 1: block maximum (scores are already in the log2 domain: q was scaled by log2e/sqrt(32))
         float mx = -INFINITY;
@@ -520,20 +568,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         for (int c = 0; c < 4; ++c) {
           tmem_ld_32x32(t_s + c * 32, v);
           tmem_ld_wait();
-          if (valid >= (c + 1) * 32) {
+          if (full) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+              if (c * 32 + j >= lo && c * 32 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
           }
         }
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx(m - m_new);  // 0 on the first block (m = -inf)
         if (kb > 0) {
           // previous P.V finished: its O block is ready and P may be overwritten
-          mbar_wait(&o_full[h], (g - 1) & 1);
+          mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
           tc_fence_after();
           tmem_ld_32x32(t_o, v);
           tmem_ld_wait();
@@ -559,8 +607,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           for (int j = 0; j < 16; ++j) {
             float a = ex2_approx(__uint_as_float(v[2 * j]) - m);
             float b = ex2_approx(__uint_as_float(v[2 * j + 1]) - m);
-            if (c * 32 + 2 * j >= valid) a = 0.f;
-            if (c * 32 + 2 * j + 1 >= valid) b = 0.f;
+            if (!full) {
+              const int k0 = c * 32 + 2 * j;
+              if (k0 < lo || k0 >= hi) a = 0.f;
+              if (k0 + 1 < lo || k0 + 1 >= hi) b = 0.f;
+            }
             pk[j] = pack_bf16x2(a, b);
             ps += bf16_lo(pk[j]) + bf16_hi(pk[j]);
           }
@@ -578,7 +629,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         if (lane == 0) mbar_arrive(&p_full[h]);
       }
       // last O block, normalise, write the context rows of this head
-      mbar_wait(&o_full[h], (g - 1) & 1);
+      mbar_wait_c(&o_full[h], (g - 1) & 1, 113u);
       tc_fence_after();
       tmem_ld_32x32(t_o, v);
       tmem_ld_wait();
@@ -738,7 +789,9 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   const int items = p.nqb * kHeadPairs;
   if (items <= 0) return cudaSuccess;
   const int grid = items < sm_count ? items : sm_count;
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, p);
+  AttnParams pd = p;
+  if (const char* dbg = getenv("FRS_ATTN_DEBUG")) pd.debug = atoi(dbg);
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, pd);
   return cudaGetLastError();
 }
 

@@ -50,13 +50,15 @@ struct QBlock {
   int32_t q_tok0;    // first token row of this query block
   int32_t seq_tok0;  // first token row of the sequence
   int32_t seq_len;
-  int32_t pad;
+  int32_t kv_tok0;   // seq_tok0 rounded down to a multiple of 8: key blocks start here (a TMA box must
+                     // start on a 16-byte boundary and tokens are the contiguous dimension of vt)
 };
 
 struct AttnParams {
   const QBlock* qblk;
   int nqb;             // work items = nqb * kHeadPairs
   __nv_bfloat16* ctx;  // [rows, 384]
+  int debug;           // fault isolation (FRS_ATTN_DEBUG): 1 skip P.V MMAs, 2 skip S MMAs, 4 skip V loads
 };
 
 size_t gemm_smem_bytes(int epi);
@@ -83,6 +85,8 @@ cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seql
 cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs, const float* wp,
                            const float* bp, const float* wc, const float* bc, float* logits,
                            cudaStream_t st);
+// mapped host words {wait code, blockIdx, parity, threadIdx} written by a barrier wait that timed out
+uint32_t* bert_trap_info_host();
 cudaError_t launch_bf16_to_f32(const __nv_bfloat16* src, int64_t n, float* dst, cudaStream_t st);
 cudaError_t launch_f32_to_bf16(const float* src, int64_t n, __nv_bfloat16* dst, cudaStream_t st);
 

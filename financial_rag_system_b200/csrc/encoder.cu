@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -261,6 +262,17 @@ extern "C" int frs_encoder_max_tokens(const frs_encoder* enc) { return enc ? enc
 // forward pass
 // ---------------------------------------------------------------------------------------------
 static int prof_mark(frs_encoder* e, int cls, cudaStream_t st) {
+  static const bool debug_sync = getenv("FRS_DEBUG_SYNC") != nullptr;
+  if (debug_sync) {  // fault isolation: name the kernel class that failed
+    static const char* names[] = {"embed_ln", "gemm<QKV>", "attention", "gemm<ResLN> out-proj", "gemm<Gelu>",
+                                  "gemm<ResLN> ffn-down", "pool/head"};
+    cudaError_t err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+      const uint32_t* ti = bert_trap_info_host();
+      return abi_set_err(FRS_E_CUDA, "kernel %s failed: %s (trap info: wait %u block %u parity %u thread %u)", names[cls],
+                         cudaGetErrorString(err), ti ? ti[0] : 0u, ti ? ti[1] : 0u, ti ? ti[2] : 0u, ti ? ti[3] : 0u);
+    }
+  }
   if (!e->prof) return FRS_OK;
   if (e->plaunches + 1 >= (int)e->pev.size()) return FRS_OK;
   e->pclass[e->plaunches] = cls;
@@ -289,7 +301,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
       b.q_tok0 = host_cu[s] + q0;
       b.seq_tok0 = host_cu[s];
       b.seq_len = len;
-      b.pad = 0;
+      b.kv_tok0 = host_cu[s] & ~7;
     }
   }
   const int M = host_cu[n_seqs];
@@ -300,6 +312,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
   CU_TRY(cudaEventRecord(e->staged, st));
   e->staged_pending = true;
   e->plaunches = 0;
+  if (getenv("FRS_DEBUG_SYNC")) bert_trap_info_host();  // arm the wait-timeout recorder
   if (e->prof) CU_TRY(cudaEventRecord(e->pev[0], st));
   int rc;
   CU_TRY(launch_positions(e->d_cu, n_seqs, e->pos_ids, st));
