@@ -80,26 +80,40 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 // positions + embeddings
 // ---------------------------------------------------------------------------------------------
-__global__ void positions_kernel(const int32_t* __restrict__ cu, int n_seqs, int32_t* __restrict__ pos) {
+__global__ void row_map_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ row_start, int n_seqs,
+                               int32_t* __restrict__ src_tok, int32_t* __restrict__ pos_of_row,
+                               int32_t* __restrict__ row_of_tok) {
   const int s = blockIdx.x;
   if (s >= n_seqs) return;
-  const int t0 = cu[s], t1 = cu[s + 1];
-  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) pos[t] = t - t0;
+  const int t0 = cu[s], len = cu[s + 1] - cu[s], r0 = row_start[s], slot = row_start[s + 1] - r0;
+  for (int i = threadIdx.x; i < slot; i += blockDim.x) {
+    src_tok[r0 + i] = i < len ? t0 + i : -1;
+    pos_of_row[r0 + i] = i;
+    if (i < len) row_of_tok[t0 + i] = r0 + i;
+  }
 }
 
-// one warp per token: 384 = 3 x (32 lanes x float4)
+// one warp per internal row: 384 = 3 x (32 lanes x float4)
 __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ type_ids,
-                const int32_t* __restrict__ pos_ids, int M, int vocab, const float* __restrict__ word,
-                const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ x) {
-  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                const int32_t* __restrict__ src_tok, const int32_t* __restrict__ pos_of_row, int M, int vocab,
+                const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                __nv_bfloat16* __restrict__ x) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (tok >= M) return;
+  if (row >= M) return;
+  const int tok = src_tok[row];
+  if (tok < 0) {  // alignment row between two sequences: keep it finite
+    uint2* out = reinterpret_cast<uint2*>(x + (size_t)row * kHid);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[lane + 32 * i] = make_uint2(0u, 0u);
+    return;
+  }
   int id = ids[tok];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
   const int tt = type_ids ? (type_ids[tok] != 0) : 0;
-  int ps = pos_ids[tok];
+  int ps = pos_of_row[row];
   ps = ps < 0 ? 0 : (ps >= kMaxSeq ? kMaxSeq - 1 : ps);
   const float4* w = reinterpret_cast<const float4*>(word + (size_t)id * kHid);
   const float4* pp = reinterpret_cast<const float4*>(pos + (size_t)ps * kHid);
@@ -123,7 +137,7 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ typ
     sq += d * d;
   }
   const float rstd = rsqrtf(warp_sum(sq) * (1.0f / kHid) + eps);
-  uint2* out = reinterpret_cast<uint2*>(x + (size_t)tok * kHid);
+  uint2* out = reinterpret_cast<uint2*>(x + (size_t)row * kHid);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
@@ -658,12 +672,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
 // pooling + L2 normalisation (sentence-transformers Pooling + Normalize), cross-encoder head
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, int n_seqs, int pool_mode,
-                      float* __restrict__ out) {
+pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu,
+                      const int32_t* __restrict__ row_start, int n_seqs, int pool_mode, float* __restrict__ out) {
   __shared__ float red[4];
   const int s = blockIdx.x;
   if (s >= n_seqs) return;
-  const int t0 = cu[s], t1 = cu[s + 1];
+  const int t0 = row_start[s], t1 = t0 + (cu[s + 1] - cu[s]);
   float v[3] = {0.f, 0.f, 0.f};
   if (pool_mode == 0) {
 #pragma unroll
@@ -687,7 +701,7 @@ pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __rest
 }
 
 __global__ void __launch_bounds__(384)
-ce_head_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, int n_seqs,
+ce_head_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ row_start, int n_seqs,
                const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ wc,
                const float* __restrict__ bc, float* __restrict__ logits) {
   __shared__ float xs[kHid];
@@ -696,7 +710,7 @@ ce_head_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ 
   const int s = blockIdx.x;
   if (s >= n_seqs) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  xs[threadIdx.x] = __bfloat162float(x[(size_t)cu[s] * kHid + threadIdx.x]);
+  xs[threadIdx.x] = __bfloat162float(x[(size_t)row_start[s] * kHid + threadIdx.x]);
   __syncthreads();
   for (int o = warp * 32; o < warp * 32 + 32; ++o) {
     const float* w = wp + (size_t)o * kHid;
@@ -717,6 +731,13 @@ ce_head_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ 
   }
 }
 
+__global__ void gather_rows_f32_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ row_of_tok,
+                                       int n_tokens, float* __restrict__ out) {
+  const int t = blockIdx.x;
+  if (t >= n_tokens) return;
+  const size_t r = (size_t)row_of_tok[t];
+  for (int i = threadIdx.x; i < kHid; i += blockDim.x) out[(size_t)t * kHid + i] = __bfloat162float(x[r * kHid + i]);
+}
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t n, float* __restrict__ dst) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __bfloat162float(src[i]);
@@ -734,18 +755,20 @@ size_t gemm_smem_bytes(int epi) {
 }
 size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
 
-cudaError_t launch_positions(const int32_t* cu_seqlens, int n_seqs, int32_t* pos_ids, cudaStream_t st) {
+cudaError_t launch_row_map(const int32_t* cu_seqlens, const int32_t* row_start, int n_seqs, int32_t* src_tok,
+                           int32_t* pos_of_row, int32_t* row_of_tok, cudaStream_t st) {
   if (n_seqs <= 0) return cudaSuccess;
-  positions_kernel<<<n_seqs, 128, 0, st>>>(cu_seqlens, n_seqs, pos_ids);
+  row_map_kernel<<<n_seqs, 128, 0, st>>>(cu_seqlens, row_start, n_seqs, src_tok, pos_of_row, row_of_tok);
   return cudaGetLastError();
 }
 
-cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* pos_ids, int M,
-                            int vocab, const float* word, const float* pos, const float* type,
-                            const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
+cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* src_tok,
+                            const int32_t* pos_of_row, int M, int vocab, const float* word, const float* pos,
+                            const float* type, const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
                             cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
-  embed_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, type_ids, pos_ids, M, vocab, word, pos, type, gamma, beta, eps, x);
+  embed_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, type_ids, src_tok, pos_of_row, M, vocab, word, pos, type, gamma,
+                                               beta, eps, x);
   return cudaGetLastError();
 }
 
@@ -795,21 +818,27 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   return cudaGetLastError();
 }
 
-cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs,
-                                  int pool_mode, float* out, cudaStream_t st) {
+cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, const int32_t* row_start,
+                                  int n_seqs, int pool_mode, float* out, cudaStream_t st) {
   if (n_seqs <= 0) return cudaSuccess;
-  pool_normalize_kernel<<<n_seqs, 128, 0, st>>>(x, cu_seqlens, n_seqs, pool_mode, out);
+  pool_normalize_kernel<<<n_seqs, 128, 0, st>>>(x, cu_seqlens, row_start, n_seqs, pool_mode, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs, const float* wp,
+cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* row_start, int n_seqs, const float* wp,
                            const float* bp, const float* wc, const float* bc, float* logits,
                            cudaStream_t st) {
   if (n_seqs <= 0) return cudaSuccess;
-  ce_head_kernel<<<n_seqs, 384, 0, st>>>(x, cu_seqlens, n_seqs, wp, bp, wc, bc, logits);
+  ce_head_kernel<<<n_seqs, 384, 0, st>>>(x, row_start, n_seqs, wp, bp, wc, bc, logits);
   return cudaGetLastError();
 }
 
+cudaError_t launch_gather_rows_f32(const __nv_bfloat16* x, const int32_t* row_of_tok, int n_tokens, float* out,
+                                   cudaStream_t st) {
+  if (n_tokens <= 0) return cudaSuccess;
+  gather_rows_f32_kernel<<<n_tokens, 128, 0, st>>>(x, row_of_tok, n_tokens, out);
+  return cudaGetLastError();
+}
 cudaError_t launch_bf16_to_f32(const __nv_bfloat16* src, int64_t n, float* dst, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);

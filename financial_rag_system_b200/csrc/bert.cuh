@@ -64,12 +64,19 @@ struct AttnParams {
 size_t gemm_smem_bytes(int epi);
 size_t attn_smem_bytes();
 
-// pos_ids[t] = t - seq_tok0 for every packed token (one block per sequence)
-cudaError_t launch_positions(const int32_t* cu_seqlens, int n_seqs, int32_t* pos_ids, cudaStream_t st);
-// x = LayerNorm(word[id] + pos[p] + type[tt]) -> bf16 ; type_ids may be null (all 0)
-cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* pos_ids, int M,
-                            int vocab, const float* word, const float* pos, const float* type,
-                            const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
+// Internal row layout: sequence s owns rows [row_start[s], row_start[s] + len_s) and row_start[s] is a
+// multiple of 8 (so that every TMA box of the transposed V starts on a 16-byte boundary, and a
+// sequence's arithmetic does not depend on where it sits in the batch).  cu_seqlens is the caller's
+// packed layout.  One block per sequence fills, for every internal row of the sequence's slot,
+// src_tok[row] (caller token index, -1 for the <= 7 alignment rows), pos_of_row[row] (position in the
+// sequence) and, for every caller token, row_of_tok[token].
+cudaError_t launch_row_map(const int32_t* cu_seqlens, const int32_t* row_start, int n_seqs, int32_t* src_tok,
+                           int32_t* pos_of_row, int32_t* row_of_tok, cudaStream_t st);
+// x[row] = LayerNorm(word[id] + pos[p] + type[tt]) -> bf16 for the M internal rows (alignment rows = 0);
+// type_ids may be null (all 0)
+cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* src_tok,
+                            const int32_t* pos_of_row, int M, int vocab, const float* word, const float* pos,
+                            const float* type, const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
                             cudaStream_t st);
 // C = A[M,K] * W[N,K]^T (+ epilogue).  tmap_a: activations, box 64 x 128, SWIZZLE_128B;
 // tmap_b: weights, box 64 x 192, SWIZZLE_128B.
@@ -79,12 +86,15 @@ cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const 
 cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_vt,
                              const AttnParams& p, cudaStream_t st);
 // pool_mode 0 = CLS row, 1 = mean over the sequence; then x / max(||x||, 1e-12)
-cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs,
-                                  int pool_mode, float* out, cudaStream_t st);
+cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, const int32_t* row_start,
+                                  int n_seqs, int pool_mode, float* out, cudaStream_t st);
 // logits[s] = wc . tanh(Wp * x[cls_s] + bp) + bc
-cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* cu_seqlens, int n_seqs, const float* wp,
+cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* row_start, int n_seqs, const float* wp,
                            const float* bp, const float* wc, const float* bc, float* logits,
                            cudaStream_t st);
+// out[t] = fp32(x[row_of_tok[t]]) for the caller's packed tokens
+cudaError_t launch_gather_rows_f32(const __nv_bfloat16* x, const int32_t* row_of_tok, int n_tokens, float* out,
+                                   cudaStream_t st);
 // mapped host words {wait code, blockIdx, parity, threadIdx} written by a barrier wait that timed out
 uint32_t* bert_trap_info_host();
 cudaError_t launch_bf16_to_f32(const __nv_bfloat16* src, int64_t n, float* dst, cudaStream_t st);

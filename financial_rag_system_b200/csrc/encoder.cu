@@ -55,11 +55,12 @@ struct frs_encoder {
   std::vector<void*> owned;  // every device allocation, freed in destroy
   // activations (packed tokens)
   __nv_bfloat16 *x0 = nullptr, *x1 = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *h = nullptr;
-  int32_t *pos_ids = nullptr, *d_cu = nullptr;
+  int32_t *pos_of_row = nullptr, *src_tok = nullptr, *row_of_tok = nullptr;
+  int32_t *d_cu = nullptr, *d_rs = nullptr;  // caller cu_seqlens | internal row starts (multiples of 8)
   QBlock* d_qblk = nullptr;
   CUtensorMap t_x0, t_x1, t_ctx, t_h, t_qk, t_vt;
   // staging
-  int32_t *h_cu = nullptr, *h_ids = nullptr, *h_type = nullptr;
+  int32_t *h_cu = nullptr, *h_rs = nullptr, *h_ids = nullptr, *h_type = nullptr;
   QBlock* h_qblk = nullptr;
   float* h_out = nullptr;
   int32_t *d_ids = nullptr, *d_type = nullptr;
@@ -82,6 +83,7 @@ static void free_encoder(frs_encoder* e) {
   cudaSetDevice(e->device);
   for (void* p : e->owned) cudaFree(p);
   cudaFreeHost(e->h_cu);
+  cudaFreeHost(e->h_rs);
   cudaFreeHost(e->h_ids);
   cudaFreeHost(e->h_type);
   cudaFreeHost(e->h_qblk);
@@ -222,13 +224,17 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   EN_TRY(dev_alloc(e, &e->vt, T * kHid * 2, true));
   EN_TRY(dev_alloc(e, &e->ctx, T * kHid * 2, true));
   EN_TRY(dev_alloc(e, &e->h, T * kFfn * 2, true));
-  EN_TRY(dev_alloc(e, &e->pos_ids, T * 4, true));
+  EN_TRY(dev_alloc(e, &e->pos_of_row, T * 4, true));
+  EN_TRY(dev_alloc(e, &e->src_tok, T * 4, true));
+  EN_TRY(dev_alloc(e, &e->row_of_tok, T * 4, true));
   EN_TRY(dev_alloc(e, &e->d_cu, ((size_t)e->max_seqs + 1) * 4, true));
+  EN_TRY(dev_alloc(e, &e->d_rs, ((size_t)e->max_seqs + 1) * 4, true));
   EN_TRY(dev_alloc(e, &e->d_qblk, (size_t)e->max_qblk * sizeof(QBlock), true));
   EN_TRY(dev_alloc(e, &e->d_ids, T * 4, true));
   EN_TRY(dev_alloc(e, &e->d_type, T * 4, true));
   EN_TRY(dev_alloc(e, &e->d_out, (size_t)e->max_seqs * kHid * 4, true));
   EN_TRY(cudaMallocHost(&e->h_cu, ((size_t)e->max_seqs + 1) * 4));
+  EN_TRY(cudaMallocHost(&e->h_rs, ((size_t)e->max_seqs + 1) * 4));
   EN_TRY(cudaMallocHost(&e->h_qblk, (size_t)e->max_qblk * sizeof(QBlock)));
   EN_TRY(cudaMallocHost(&e->h_ids, T * 4));
   EN_TRY(cudaMallocHost(&e->h_type, T * 4));
@@ -289,25 +295,30 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
   if (host_cu[0] != 0) return abi_set_err(FRS_E_INVALID, "cu_seqlens[0] must be 0");
   // the pinned staging buffers are reused: wait for the previous call's copies
   if (e->staged_pending) CU_TRY(cudaEventSynchronize(e->staged));
-  int nqb = 0;
+  // internal layout: every sequence starts on a row that is a multiple of 8 (see bert.cuh)
+  int nqb = 0, row = 0;
   for (int s = 0; s < n_seqs; ++s) {
     const int len = host_cu[s + 1] - host_cu[s];
     if (len < 1 || len > kMaxSeq)
       return abi_set_err(FRS_E_INVALID, "sequence %d has %d tokens; must be in [1,%d]", s, len, kMaxSeq);
-    if (host_cu[s + 1] > e->max_tokens)
-      return abi_set_err(FRS_E_CAPACITY, "batch has more than max_tokens = %d packed tokens", e->max_tokens);
+    e->h_rs[s] = row;
+    if (row + len > e->max_tokens)
+      return abi_set_err(FRS_E_CAPACITY, "batch does not fit the workspace (max_tokens = %d, sequences are padded to a multiple of 8 rows)", e->max_tokens);
     for (int q0 = 0; q0 < len; q0 += kBM) {
       QBlock& b = e->h_qblk[nqb++];
-      b.q_tok0 = host_cu[s] + q0;
-      b.seq_tok0 = host_cu[s];
+      b.q_tok0 = row + q0;
+      b.seq_tok0 = row;
       b.seq_len = len;
-      b.kv_tok0 = host_cu[s] & ~7;
+      b.kv_tok0 = row;
     }
+    row += (len + 7) & ~7;
   }
-  const int M = host_cu[n_seqs];
+  e->h_rs[n_seqs] = row;
+  const int M = row < e->max_tokens ? row : e->max_tokens;  // internal rows
   memcpy(e->h_cu, host_cu, ((size_t)n_seqs + 1) * 4);
   CU_TRY(cudaStreamWaitEvent(st, e->ws_free, 0));
   CU_TRY(cudaMemcpyAsync(e->d_cu, e->h_cu, ((size_t)n_seqs + 1) * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(e->d_rs, e->h_rs, ((size_t)n_seqs + 1) * 4, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(e->d_qblk, e->h_qblk, (size_t)nqb * sizeof(QBlock), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaEventRecord(e->staged, st));
   e->staged_pending = true;
@@ -315,8 +326,8 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
   if (getenv("FRS_DEBUG_SYNC")) bert_trap_info_host();  // arm the wait-timeout recorder
   if (e->prof) CU_TRY(cudaEventRecord(e->pev[0], st));
   int rc;
-  CU_TRY(launch_positions(e->d_cu, n_seqs, e->pos_ids, st));
-  CU_TRY(launch_embed_ln(d_ids, d_type, e->pos_ids, M, e->cfg.vocab_size, e->word, e->pos, e->type, e->emb_g,
+  CU_TRY(launch_row_map(e->d_cu, e->d_rs, n_seqs, e->src_tok, e->pos_of_row, e->row_of_tok, st));
+  CU_TRY(launch_embed_ln(d_ids, d_type, e->src_tok, e->pos_of_row, M, e->cfg.vocab_size, e->word, e->pos, e->type, e->emb_g,
                          e->emb_b, e->cfg.ln_eps, e->x0, st));
   if ((rc = prof_mark(e, kPEmbed, st))) return rc;
   const int mtiles = (M + kBM - 1) / kBM;
@@ -369,7 +380,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, g, st));
     if ((rc = prof_mark(e, kPDown, st))) return rc;
   }
-  e->last_tokens = M;
+  e->last_tokens = host_cu[n_seqs];
   return FRS_OK;
 }
 
@@ -382,7 +393,7 @@ extern "C" int frs_encoder_embed(frs_encoder* enc, const int32_t* dev_ids, const
   cudaStream_t st = (cudaStream_t)stream;
   int rc = forward(enc, dev_ids, nullptr, host_cu_seqlens, n_seqs, st);
   if (rc) return rc;
-  CU_TRY(launch_pool_normalize(enc->x0, enc->d_cu, n_seqs, pool_mode, dev_out, st));
+  CU_TRY(launch_pool_normalize(enc->x0, enc->d_cu, enc->d_rs, n_seqs, pool_mode, dev_out, st));
   if ((rc = prof_mark(enc, kPHead, st))) return rc;
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;
@@ -398,7 +409,7 @@ extern "C" int frs_encoder_score_pairs(frs_encoder* enc, const int32_t* dev_ids,
   cudaStream_t st = (cudaStream_t)stream;
   int rc = forward(enc, dev_ids, dev_type_ids, host_cu_seqlens, n_seqs, st);
   if (rc) return rc;
-  CU_TRY(launch_ce_head(enc->x0, enc->d_cu, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
+  CU_TRY(launch_ce_head(enc->x0, enc->d_rs, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
   if ((rc = prof_mark(enc, kPHead, st))) return rc;
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;
@@ -419,9 +430,14 @@ static int run_host(frs_encoder* enc, const int32_t* host_ids, const int32_t* ho
   std::vector<int32_t> cu;
   int s0 = 0;
   while (s0 < n_seqs) {
-    int s1 = s0;
+    int s1 = s0, rows = 0;
     const int base = host_cu[s0];
-    while (s1 < n_seqs && s1 - s0 < enc->max_seqs && host_cu[s1 + 1] - base <= enc->max_tokens) ++s1;
+    while (s1 < n_seqs && s1 - s0 < enc->max_seqs) {
+      const int len = host_cu[s1 + 1] - host_cu[s1];
+      if (rows + len > enc->max_tokens) break;
+      rows += (len + 7) & ~7;  // internal layout: sequences start on multiples of 8 rows
+      ++s1;
+    }
     if (s1 == s0) return abi_set_err(FRS_E_INVALID, "sequence %d is longer than max_tokens", s0);
     const int ntok = host_cu[s1] - base;
     cu.resize((size_t)(s1 - s0) + 1);
@@ -461,7 +477,8 @@ extern "C" int frs_encoder_last_hidden(frs_encoder* enc, float* dev_out, int n_t
   std::lock_guard<std::mutex> lk(enc->mu);
   cudaStream_t st = (cudaStream_t)stream;
   CU_TRY(cudaStreamWaitEvent(st, enc->ws_free, 0));
-  CU_TRY(launch_bf16_to_f32(enc->x0, (int64_t)n_tokens * kHid, dev_out, st));
+  if (n_tokens > enc->last_tokens) return abi_set_err(FRS_E_INVALID, "the last pass had %d tokens", enc->last_tokens);
+  CU_TRY(launch_gather_rows_f32(enc->x0, enc->row_of_tok, n_tokens, dev_out, st));
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;
 }

@@ -196,7 +196,8 @@ typedef struct frs_bert_cfg {
 #define FRS_BERT_WEIGHTS(layers, has_head) (5 + 16 * (layers) + ((has_head) ? 4 : 0))
 
 /* weights: array of n_weights pointers (host memory if !on_device, else device memory of `device`).
- * max_tokens: packed tokens one forward pass can hold (workspace is ~7.7 KB per token). */
+ * max_tokens: token rows one forward pass can hold (workspace is ~7.7 KB per row); internally every
+ * sequence starts on a row that is a multiple of 8, so a pass holds sum roundup8(len_s) <= max_tokens. */
 int frs_encoder_create(int device, const frs_bert_cfg* cfg, const float* const* weights, int n_weights,
                        int on_device, int max_tokens, frs_encoder** out);
 int frs_encoder_destroy(frs_encoder* enc);
@@ -223,7 +224,8 @@ int frs_encoder_last_hidden(frs_encoder* enc, float* dev_out, int n_tokens, void
 /* diagnostics: the first n_elems bf16 values of a workspace buffer of the most recent pass, widened
  * to fp32.  which: 0 x0 [T,384] (layer output), 1 x1 [T,384] (after attention block), 2 qk [T,768]
  * (scaled q | k), 3 vt [384,T] (v transposed, T = max_tokens), 4 ctx [T,384], 5 h [T,1536].
- * With a 1-layer model this exposes every stage of a layer.  Test aid, not a product path. */
+ * With a 1-layer model this exposes every stage of a layer.  Rows are in the library's internal
+ * layout: sequence s starts at row sum_{j<s} roundup8(len_j).  Test aid, not a product path. */
 int frs_encoder_debug_read(frs_encoder* enc, int which, float* dev_out, int64_t n_elems, void* stream);
 /* Profiling (off by default): CUDA events around every kernel of a forward pass.  read_profile
  * synchronises and returns the milliseconds of the LAST pass per kernel class:
