@@ -68,8 +68,40 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
-__device__ __forceinline__ float gelu_erf(float x) {  // modeling_bert.py:339-342, hidden_act="gelu"
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+// erf(x) as an odd rational function x P(x^2) / Q(x^2) on [-4, 4] (|erf| = 1 beyond in fp32): the
+// single-precision fit used by Eigen/XLA, max abs error 6.5e-8 against scipy.special.erf — far below
+// fp32 rounding of the result.  13 FMA + 1 reciprocal, no branches (erff() is ~2x the instructions,
+// and this epilogue is issue-bound).
+__device__ __forceinline__ float erf_rational(float x) {
+  x = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float x2 = x * x;
+  float p = fmaf(x2, -2.72614225801306e-10f, 2.77068142495902e-08f);
+  p = fmaf(x2, p, -2.10102402082508e-06f);
+  p = fmaf(x2, p, -5.69250639462346e-05f);
+  p = fmaf(x2, p, -7.34990630326855e-04f);
+  p = fmaf(x2, p, -2.95459980854025e-03f);
+  p = fmaf(x2, p, -1.60960333262415e-02f);
+  float q = fmaf(x2, -1.45660718464996e-05f, -2.13374055278905e-04f);
+  q = fmaf(x2, q, -1.68282697438203e-03f);
+  q = fmaf(x2, q, -7.37332916720468e-03f);
+  q = fmaf(x2, q, -1.42647390514189e-02f);
+  return __fdividef(x * p, q);
+}
+// GELU(x) = x Phi(x)  (modeling_bert.py:339-342, hidden_act="gelu" = the erf form).
+// Default: Phi(x) = (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) / 2 with the inner polynomial fitted to the
+// exact erf form (max |error| 2.5e-5 over the whole real line, scripts/fit_gelu.py) and MUFU tanh
+// (relative error 2^-11): at most ~|x| 2.7e-4 in total, an eighth of the bf16 rounding step of the
+// stored result — 8 instructions per element instead of 20.  -DFRS_EXACT_GELU selects the erf form.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float hx = 0.5f * x;
+#ifdef FRS_EXACT_GELU
+  return fmaf(hx, erf_rational(x * 0.70710678118654752f), hx);
+#else
+  const float x2 = x * x;
+  float u = fmaf(x2, -0.00035151678934123415f, 0.03700564602521096f);
+  u = fmaf(x2, u, 0.7975078842799184f);
+  return fmaf(hx, tanh_approx(x * u), hx);
+#endif
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -164,26 +196,36 @@ struct GemmCfg {
   static constexpr int kStageA = kBM * 128;    // 128 rows x 64 bf16
   static constexpr int kStageB = BN * 128;     // BN rows x 64 bf16
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN == 192 ? 5 : 3;
+  static constexpr int kStages = BN == 192 ? 4 : 2;
   static constexpr int kAcc = BN == 192 ? 2 : 1;  // TMEM accumulator stages (2 x 192 or 1 x 384 columns)
   static constexpr int kNSplit = BN / kNSub;
   static constexpr int kColsPerThread = BN / 2;   // two epilogue warps share a TMEM lane quarter
   static constexpr int kRing = kStages * kStage;
-  static constexpr int kParF = kRing;                  // fp32 params: bias[1536] | gamma[384] | beta[384]
-  static constexpr int kStat = kParF + (1536 + 768) * 4;  // float2 [2 parity][2 halves][128 rows]
-  static constexpr int kBars = kStat + 2 * 2 * 128 * 8;
+  static constexpr int kOut = kRing;                   // output staging for the TMA stores
+  static constexpr int kOutBytes = kBM * kNSub * 2;    // 48 KB: 128 x 192 bf16
+  static constexpr int kOutBufs = 1;  // (a second buffer costs a ring stage and measured slower)
+  static constexpr int kParF = kOut + kOutBufs * kOutBytes;  // fp32 params: bias[1536] | gamma[384] | beta[384]
+  static constexpr int kStat = kParF + (1536 + 768) * 4;  // float2 [2 parity][2 halves][128 rows] (ResLN only)
+  static constexpr int kBars = kStat + (BN == 384 ? 2 * 2 * 128 * 8 : 0);
   static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc) * 8;
   static constexpr int kTotal = kHolder + 16;
 };
 
+// Output path of every epilogue: registers -> swizzled staging tile in shared memory -> TMA store.
+// (Direct per-thread row stores cost one 16-byte LSU transaction per lane; the staged tile leaves as
+// full 128-byte lines.)  Named barriers 2 / 3 = "staging is free" / "staging is written".
+constexpr uint32_t kBarStageFree = 2, kBarStageFull = 3;
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const GemmParams p) {
   using C = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = sm;
+  uint8_t* sout0 = sm + C::kOut;
   float* sbias = reinterpret_cast<float*>(sm + C::kParF);
   float* sgamma = sbias + 1536;
   float* sbeta = sgamma + 384;
@@ -284,6 +326,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t quarter = warp & 3;           // TMEM lanes 32*quarter .. +32 are visible to this warp
     const uint32_t half = (warp - 2) >> 2;       // which half of the tile's columns
     const uint32_t row = quarter * 32 + lane;    // row within the tile
+    const bool issuer = threadIdx.x == 64;       // the epilogue thread that owns the TMA store groups
+    if (issuer) {
+      tma_prefetch_desc(&tmap_out);
+      if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
+    }
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int mt = tile / nt_count, nt = tile % nt_count;
@@ -291,27 +338,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t aph = (lt / C::kAcc) & 1;
       const int grow = mt * kBM + (int)row;
       const bool live = grow < p.M;
+      // ResLN: this thread's 192 residual values are fetched BEFORE the accumulator is waited for, so
+      // their global-memory latency hides behind the tile's MMA main loop
+      uint4 rres[EPI == kEpiResLN ? C::kColsPerThread / 8 : 1];
+      if constexpr (EPI == kEpiResLN) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)grow * kHid + half * C::kColsPerThread);
+#pragma unroll
+        for (int j = 0; j < C::kColsPerThread / 8; ++j) rres[j] = live ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+      }
       mbar_wait_c(&tfull[acc], aph, 104u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN + half * C::kColsPerThread;
       uint32_t v[32];
-      if constexpr (EPI == kEpiQKV || EPI == kEpiGelu) {
+      if (p.debug & 1) {
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      } else if constexpr (EPI == kEpiQKV || EPI == kEpiGelu) {
+        const bool transposed = EPI == kEpiQKV && nt * BN >= 2 * kHid;  // value projection
+        uint8_t* sout = sout0;
+        if (issuer) tma_store_wait_read<0>();  // the previous tile's stores have read the staging tile
+        named_bar_sync(kBarStageFree, kGemmEpiThreads);
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
-          const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // global output column
+          const int ct = (int)half * C::kColsPerThread + c * 32;  // column within the tile
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (!live) continue;
-          const float* bs = sbias + col;
-          if (EPI == kEpiQKV && col >= 2 * kHid) {
+          if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained: the next tile's MMAs may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const float* bs = sbias + nt * BN + ct;
+          if (p.debug & 4) continue;
+          if (transposed) {
             // value projection: stored transposed, vt[dim][token], so that it is the K-major B operand
-            // of P.V in the attention kernel
-            __nv_bfloat16* dst = p.vt + (size_t)(col - 2 * kHid) * p.vt_ld + grow;
+            // of P.V in the attention kernel.  Staging boxes: [64 dims][64 tokens], SWIZZLE_128B.
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              dst[(size_t)j * p.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t d = (uint32_t)ct + j;
+              uint8_t* dst = sout + ((d >> 6) * 2 + (row >> 6)) * 8192 + (d & 63) * 128 +
+                             ((((row & 63) >> 3) ^ (d & 7)) << 4) + (row & 7) * 2;
+              *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
+            }
           } else {
-            const float sc = (EPI == kEpiQKV && col < kHid) ? p.qscale : 1.0f;
+            const float sc = (EPI == kEpiQKV && nt * BN < kHid) ? p.qscale : 1.0f;
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -326,30 +399,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
               o[j] = pack_bf16x2(a, b);
             }
-            const int ld = EPI == kEpiQKV ? 2 * kHid : p.N;
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)grow * ld + col);
+            // staging boxes: [128 rows][64 columns], SWIZZLE_128B
+            uint8_t* box = sout + (ct >> 6) * 16384 + row * 128;
+            const uint32_t j0 = (uint32_t)(ct & 63) >> 3;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(box + (((j0 + j) ^ (row & 7)) << 4)) =
+                  make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           }
+        }
+        fence_proxy_async();
+        named_bar_sync(kBarStageFull, kGemmEpiThreads);
+        if (issuer && !(p.debug & 2)) {
+          if (transposed) {
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+              tma_store_2d(&tmap_out2, sout + b * 8192, mt * kBM + (b & 1) * 64, nt * BN - 2 * kHid + (b >> 1) * 64);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) tma_store_2d(&tmap_out, sout + b * 16384, nt * BN + b * 64, mt * kBM);
+          }
+          tma_store_commit();
         }
       } else {
         // bias + residual, row statistics; the pre-LayerNorm value goes back to TMEM (fp32)
         float sum = 0.f, sq = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
           const int col = (int)half * C::kColsPerThread + c * 32;
           tmem_ld_32x32(taddr + c * 32, v);
-          uint4 r[4];
-          if (live) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)grow * kHid + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) r[j] = rp[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) r[j] = make_uint4(0, 0, 0, 0);
-          }
           tmem_ld_wait();
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(r);
+          const uint32_t rw[16] = {rres[4 * c].x,     rres[4 * c].y,     rres[4 * c].z,     rres[4 * c].w,
+                                   rres[4 * c + 1].x, rres[4 * c + 1].y, rres[4 * c + 1].z, rres[4 * c + 1].w,
+                                   rres[4 * c + 2].x, rres[4 * c + 2].y, rres[4 * c + 2].z, rres[4 * c + 2].w,
+                                   rres[4 * c + 3].x, rres[4 * c + 3].y, rres[4 * c + 3].z, rres[4 * c + 3].w};
           const float* bs = sbias + col;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -370,29 +453,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const float mean = (sum + other.x) * (1.0f / kHid);
         const float var = fmaxf((sq + other.y) * (1.0f / kHid) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
+        // normalise and store in two rounds of 3 column chunks: staging boxes [128 rows][32 columns],
+        // SWIZZLE_64B, box (half, chunk % 3)
+        uint8_t* sout = sout0;
 #pragma unroll 1
-        for (int c = 0; c < C::kColsPerThread / 32; ++c) {
-          const int col = (int)half * C::kColsPerThread + c * 32;
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (!live) continue;
-          uint32_t o[16];
+        for (int round = 0; round < 2; ++round) {
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(kBarStageFree, kGemmEpiThreads);
+#pragma unroll 1
+          for (int cc = 0; cc < 3; ++cc) {
+            const int c = round * 3 + cc;
+            const int col = (int)half * C::kColsPerThread + c * 32;
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (c == C::kColsPerThread / 32 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * sgamma[col + 2 * j] + sbeta[col + 2 * j];
-            const float b =
-                (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
-            o[j] = pack_bf16x2(a, b);
+            for (int j = 0; j < 16; ++j) {
+              const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * sgamma[col + 2 * j] + sbeta[col + 2 * j];
+              const float b =
+                  (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
+              o[j] = pack_bf16x2(a, b);
+            }
+            uint8_t* box = sout + (half * 3 + cc) * 8192 + row * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(box + ((j ^ ((row >> 1) & 3)) << 4)) =
+                  make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)grow * kHid + col);
+          fence_proxy_async();
+          named_bar_sync(kBarStageFull, kGemmEpiThreads);
+          if (issuer) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            for (int b = 0; b < 6; ++b)
+              tma_store_2d(&tmap_out, sout + b * 8192, (b / 3) * C::kColsPerThread + (round * 3 + b % 3) * 32, mt * kBM);
+            tma_store_commit();
+          }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (issuer) tma_store_wait<0>();  // shared memory must outlive the last store
   }
   tc_fence_before();
   __syncthreads();
@@ -405,8 +509,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // Q and K of a head pair are 64 contiguous bf16 of a qk row = one 128-byte SWIZZLE_128B row; a head
 // is selected by starting the MMA's K slices 64 bytes into the row.  V is read from its transposed
 // copy vt[dim][token] so that keys are the K dimension of P.V.
-constexpr int kAttnSoftmaxWarps = 8;  // 4 per head of the pair
-constexpr int kAttnThreads = 64 + 32 * kAttnSoftmaxWarps;
+// Warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}; warpgroups 1 and 2 = the softmax threads of
+// head 0 / head 1 of the pair.  A softmax thread keeps a whole 128-key score row plus its 32-wide
+// output accumulator in registers, so the register file is re-divided at kernel start
+// (setmaxnreg): 40 per thread for warpgroup 0, 232 for the softmax warpgroups.
+constexpr int kAttnThreads = 384;
+constexpr int kAttnRegsLow = 64;
+constexpr int kAttnRegsHigh = 216;
 constexpr int kKB = 128;              // keys per block
 constexpr int kKVStages = 3;
 constexpr int kQBytes = kBM * 128;            // 128 queries x 64 dims
@@ -470,7 +579,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *holder;
   // TMEM columns: S of head h at [128h, 128h+128), O block of head h at [256+32h, +32)
-
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAttnRegsLow));
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -488,14 +598,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const uint32_t stage = g % kKVStages;
           mbar_wait_c(&kv_empty[stage], ((g / kKVStages) & 1) ^ 1, 106u);
-          mbar_arrive_expect_tx(&kv_full[stage], (p.debug & 4) ? kKBytes : kKVBytes);
+          mbar_arrive_expect_tx(&kv_full[stage], kKVBytes);
           uint8_t* dst = sm + AttnSmem::kv + (size_t)stage * kKVBytes;
           const int tok = qb.kv_tok0 + kb * kKB;
           tma_load_2d(dst, &tmap_qk, &kv_full[stage], kHid + hp * 64, tok, kEvictNormal);
-          if (!(p.debug & 4)) {
-            tma_load_2d(dst + kKBytes, &tmap_vt, &kv_full[stage], tok, hp * 64, kEvictNormal);
-            tma_load_2d(dst + kKBytes + kVSlab, &tmap_vt, &kv_full[stage], tok + 64, hp * 64, kEvictNormal);
-          }
+          tma_load_2d(dst + kKBytes, &tmap_vt, &kv_full[stage], tok, hp * 64, kEvictNormal);
+          tma_load_2d(dst + kKBytes + kVSlab, &tmap_vt, &kv_full[stage], tok + 64, hp * 64, kEvictNormal);
         }
       }
     }
@@ -504,55 +612,86 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(1u, kBM, kKB);        // S = Q K^T : 128 x 128
       constexpr uint32_t idesc_o = make_idesc(1u, kBM, kHeadDim);   // O = P V   : 128 x 32
-      uint32_t li = 0, g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-        const QBlock qb = p.qblk[item / kHeadPairs];
-        const uint32_t qbuf = li & 1;
-        mbar_wait_c(&q_full[qbuf], (li >> 1) & 1, 107u);
-        const uint32_t q_addr = smem_u32(sm + AttnSmem::q + qbuf * kQBytes);
-        const int nkb = (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const uint32_t stage = g % kKVStages;
-          mbar_wait_c(&kv_full[stage], (g / kKVStages) & 1, 108u);
-          const uint32_t k_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes);
-          const uint32_t v_addr = k_addr + kKBytes;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait_c(&s_free[h], (g & 1) ^ 1, 109u);  // softmax warps have read the previous S of this head
-            tc_fence_after();
-            const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
-            const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
-            if (!(p.debug & 2)) {
-              tc_mma<false>(tmem_base + 128 * h, da, db, idesc_s, 0u);
-              tc_mma<false>(tmem_base + 128 * h, da + 2, db + 2, idesc_s, 1u);
-            }
-            tc_commit(&s_full[h]);
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait_c(&p_full[h], g & 1, 110u);  // P of this block is in shared memory, previous O block was read
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sm + AttnSmem::pp + h * kPBytes);
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              const uint64_t da = make_desc_sw128(p_addr + s * kPSlab);
-              const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
-              if (p.debug & 1) continue;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                tc_mma<false>(tmem_base + 256 + 32 * h, da + 2 * kk, db + 2 * kk, idesc_o, (uint32_t)((s | kk) != 0));
-            }
-            tc_commit(&o_full[h]);
-          }
-          tc_commit(&kv_empty[stage]);
+      // Two cursors over this CTA's (item, key block) sequence: the score MMAs run one block AHEAD of
+      // the P.V MMAs, so that S(g+1) is computed while the softmax warps are still exponentiating S(g)
+      // (they release S as soon as it is in their registers).
+      struct Cursor {
+        int item, kb, nkb;
+        uint32_t li, g;
+      };
+      auto load_item = [&](Cursor& c) {
+        if (c.item < n_items) {
+          const QBlock qb = p.qblk[c.item / kHeadPairs];
+          c.nkb = (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB;
         }
-        tc_commit(&q_empty[qbuf]);
+      };
+      auto advance = [&](Cursor& c) {
+        ++c.g;
+        if (++c.kb == c.nkb) {
+          c.kb = 0;
+          c.item += gridDim.x;
+          ++c.li;
+          load_item(c);
+        }
+      };
+      auto issue_scores = [&](const Cursor& c) {
+        const uint32_t qbuf = c.li & 1;
+        if (c.kb == 0) mbar_wait_c(&q_full[qbuf], (c.li >> 1) & 1, 107u);
+        const uint32_t stage = c.g % kKVStages;
+        mbar_wait_c(&kv_full[stage], (c.g / kKVStages) & 1, 108u);
+        const uint32_t q_addr = smem_u32(sm + AttnSmem::q + qbuf * kQBytes);
+        const uint32_t k_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_c(&s_free[h], (c.g & 1) ^ 1, 109u);  // softmax warps hold the previous S of this head in registers
+          tc_fence_after();
+          const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
+          const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
+          tc_mma<false>(tmem_base + 128 * h, da, db, idesc_s, 0u);
+          tc_mma<false>(tmem_base + 128 * h, da + 2, db + 2, idesc_s, 1u);
+          tc_commit(&s_full[h]);
+        }
+      };
+      Cursor cs{(int)blockIdx.x, 0, 0, 0u, 0u}, cp{(int)blockIdx.x, 0, 0, 0u, 0u};
+      load_item(cs);
+      load_item(cp);
+      if (cs.item < n_items) {
+        issue_scores(cs);
+        advance(cs);
+      }
+      while (cp.item < n_items) {
+        if (cs.item < n_items) {
+          issue_scores(cs);  // S(g+1): waits until S(g) has been read, not until P(g) is written
+          advance(cs);
+        }
+        const uint32_t stage = cp.g % kKVStages;
+        const uint32_t v_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes) + kKBytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_c(&p_full[h], cp.g & 1, 110u);  // P of this block is in shared memory, previous O block was read
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(sm + AttnSmem::pp + h * kPBytes);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint64_t da = make_desc_sw128(p_addr + s * kPSlab);
+            const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma<false>(tmem_base + 256 + 32 * h, da + 2 * kk, db + 2 * kk, idesc_o, (uint32_t)((s | kk) != 0));
+          }
+          tc_commit(&o_full[h]);
+        }
+        tc_commit(&kv_empty[stage]);
+        if (cp.kb == cp.nkb - 1) tc_commit(&q_empty[cp.li & 1]);
+        advance(cp);
       }
     }
+  }
   } else {
     // ===================== softmax + output =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kAttnRegsHigh));
     const uint32_t quarter = warp & 3;
-    const uint32_t h = (warp - 2) >> 2;
+    const uint32_t h = (warp >> 2) - 1;
     const uint32_t row = quarter * 32 + lane;
     const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + 128 * h;
     const uint32_t t_o = tmem_base + ((quarter * 32u) << 16) + 256 + 32 * h;
@@ -568,7 +707,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       float o[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[j] = 0.f;
-      uint32_t v[32];
+      uint32_t s0[32], s1[32], s2[32], s3[32];  // one score row of the block: a single pass over TMEM
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         // keys [lo, hi) of this block belong to the sequence (hi - lo >= 1)
         const int lo = kb == 0 ? key_off : 0;
@@ -576,67 +715,73 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const bool full = lo == 0 && hi == kKB;
         mbar_wait_c(&s_full[h], g & 1, 111u);
         tc_fence_after();
-        // pass 1: block maximum (scores are already in the log2 domain: q was scaled by log2e/sqrt(32))
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_32x32(t_s + c * 32, v);
-          tmem_ld_wait();
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-          } else {
+        tmem_ld_32x32(t_s, s0);
+        tmem_ld_32x32(t_s + 32, s1);
+        tmem_ld_32x32(t_s + 64, s2);
+        tmem_ld_32x32(t_s + 96, s3);
+        tmem_ld_wait();
+        // S is in registers: the MMA warp may already compute the next block's scores into it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[h]);
+        if (!full) {
+          auto mask = [&](uint32_t(&sv)[32], int c) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c * 32 + j >= lo && c * 32 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
-          }
+              if (c * 32 + j < lo || c * 32 + j >= hi) sv[j] = 0xff800000u;  // -inf
+          };
+          mask(s0, 0);
+          mask(s1, 1);
+          mask(s2, 2);
+          mask(s3, 3);
         }
-        const float m_new = fmaxf(m, mx);
+        // block maximum (scores are already in the log2 domain: q was scaled by log2e/sqrt(32))
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          mx0 = fmaxf(mx0, __uint_as_float(s0[j]));
+          mx1 = fmaxf(mx1, __uint_as_float(s1[j]));
+          mx2 = fmaxf(mx2, __uint_as_float(s2[j]));
+          mx3 = fmaxf(mx3, __uint_as_float(s3[j]));
+        }
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
         const float alpha = ex2_approx(m - m_new);  // 0 on the first block (m = -inf)
         if (kb > 0) {
           // previous P.V finished: its O block is ready and P may be overwritten
           mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
           tc_fence_after();
-          tmem_ld_32x32(t_o, v);
+          uint32_t ob[32];
+          tmem_ld_32x32(t_o, ob);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = (o[j] + __uint_as_float(v[j])) * alpha;
+          for (int j = 0; j < 32; ++j) o[j] = (o[j] + __uint_as_float(ob[j])) * alpha;
           l *= alpha;
         }
         m = m_new;
-        // pass 2: p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_32x32(t_s + c * 32, v);
-          tmem_ld_wait();
-          if (c == 3) {
-            // last read of S: the MMA warp may overwrite it with the next block's scores
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[h]);
-          }
+        // p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V); masked keys give 0
+        float ps0 = 0.f, ps1 = 0.f;
+        auto expo = [&](uint32_t(&sv)[32], int c) {
           uint32_t pk[16];
-          float ps = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a = ex2_approx(__uint_as_float(v[2 * j]) - m);
-            float b = ex2_approx(__uint_as_float(v[2 * j + 1]) - m);
-            if (!full) {
-              const int k0 = c * 32 + 2 * j;
-              if (k0 < lo || k0 >= hi) a = 0.f;
-              if (k0 + 1 < lo || k0 + 1 >= hi) b = 0.f;
-            }
+            const float a = ex2_approx(__uint_as_float(sv[2 * j]) - m);
+            const float b = ex2_approx(__uint_as_float(sv[2 * j + 1]) - m);
+            ps0 += a;
+            ps1 += b;
             pk[j] = pack_bf16x2(a, b);
-            ps += bf16_lo(pk[j]) + bf16_hi(pk[j]);
           }
-          l += ps;
           uint8_t* slab = prow + (c >> 1) * kPSlab;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t chunk = ((uint32_t)((c & 1) * 4 + j)) ^ sw;
             *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
-        }
+        };
+        expo(s0, 0);
+        expo(s1, 1);
+        expo(s2, 2);
+        expo(s3, 3);
+        l += ps0 + ps1;
         fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncwarp();
@@ -645,6 +790,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       // last O block, normalise, write the context rows of this head
       mbar_wait_c(&o_full[h], (g - 1) & 1, 113u);
       tc_fence_after();
+      uint32_t v[32];
       tmem_ld_32x32(t_o, v);
       tmem_ld_wait();
       const int qi = qb.q_tok0 - qb.seq_tok0 + (int)row;  // position of this query in its sequence
@@ -773,8 +919,8 @@ cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const i
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                                 cudaStream_t st) {
+static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                                 const CUtensorMap& to2, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
   const size_t smem = GemmCfg<BN>::kTotal + 1024;
   if (!configured) {
@@ -786,16 +932,20 @@ static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUte
   const int tiles = p.num_mtiles * (p.N / BN);
   if (tiles <= 0) return cudaSuccess;
   const int grid = tiles < sm_count ? tiles : sm_count;
-  gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+  GemmParams pd = p;
+  static const int dbg = getenv("FRS_GEMM_DEBUG") ? atoi(getenv("FRS_GEMM_DEBUG")) : 0;
+  pd.debug = dbg;
+  gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, to, to2, pd);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
-                        const GemmParams& p, cudaStream_t st) {
+                        const CUtensorMap& tmap_out, const CUtensorMap& tmap_out2, const GemmParams& p,
+                        cudaStream_t st) {
   switch (epi) {
-    case kEpiQKV: return launch_gemm_t<192, kEpiQKV>(sm_count, tmap_a, tmap_b, p, st);
-    case kEpiGelu: return launch_gemm_t<192, kEpiGelu>(sm_count, tmap_a, tmap_b, p, st);
-    case kEpiResLN: return launch_gemm_t<384, kEpiResLN>(sm_count, tmap_a, tmap_b, p, st);
+    case kEpiQKV: return launch_gemm_t<192, kEpiQKV>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
+    case kEpiGelu: return launch_gemm_t<192, kEpiGelu>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
+    case kEpiResLN: return launch_gemm_t<384, kEpiResLN>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -812,9 +962,7 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   const int items = p.nqb * kHeadPairs;
   if (items <= 0) return cudaSuccess;
   const int grid = items < sm_count ? items : sm_count;
-  AttnParams pd = p;
-  if (const char* dbg = getenv("FRS_ATTN_DEBUG")) pd.debug = atoi(dbg);
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, pd);
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, p);
   return cudaGetLastError();
 }
 

@@ -35,14 +35,12 @@ struct GemmParams {
   int num_mtiles;  // ceil(M / 128)
   int N, K;
   const float* bias;   // [N]
-  __nv_bfloat16* out;  // QKV: qk [rows, 768]; GELU: [rows, N]; ResLN: [rows, 384]
-  __nv_bfloat16* vt;   // QKV only: [384, vt_ld]
-  int64_t vt_ld;
   float qscale;
   const __nv_bfloat16* resid;  // ResLN only: [rows, 384]
   const float* gamma;
   const float* beta;
   float eps;
+  int debug;  // FRS_GEMM_DEBUG (measurement aid): 1 = epilogue only drains TMEM (no math, no stores)
 };
 
 // one entry per (sequence, 128-query block)
@@ -58,7 +56,6 @@ struct AttnParams {
   const QBlock* qblk;
   int nqb;             // work items = nqb * kHeadPairs
   __nv_bfloat16* ctx;  // [rows, 384]
-  int debug;           // fault isolation (FRS_ATTN_DEBUG): 1 skip P.V MMAs, 2 skip S MMAs, 4 skip V loads
 };
 
 size_t gemm_smem_bytes(int epi);
@@ -79,9 +76,13 @@ cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const i
                             const float* type, const float* gamma, const float* beta, float eps, __nv_bfloat16* x,
                             cudaStream_t st);
 // C = A[M,K] * W[N,K]^T (+ epilogue).  tmap_a: activations, box 64 x 128, SWIZZLE_128B;
-// tmap_b: weights, box 64 x 192, SWIZZLE_128B.
+// tmap_b: weights, box 64 x 192, SWIZZLE_128B.  Outputs leave through TMA stores:
+//   QKV    tmap_out  = qk [rows, 768], box 64 x 128 SWIZZLE_128B;  tmap_out2 = vt [384, rows], box 64 x 64 SWIZZLE_128B
+//   GELU   tmap_out  = h [rows, 1536], box 64 x 128 SWIZZLE_128B   (tmap_out2 unused)
+//   ResLN  tmap_out  = x [rows, 384],  box 32 x 128 SWIZZLE_64B    (tmap_out2 unused)
 cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
-                        const GemmParams& p, cudaStream_t st);
+                        const CUtensorMap& tmap_out, const CUtensorMap& tmap_out2, const GemmParams& p,
+                        cudaStream_t st);
 // tmap_qk: qk [rows, 768], box 64 x 128; tmap_vt: vt [384, rows], box 64 x 64; both SWIZZLE_128B
 cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_vt,
                              const AttnParams& p, cudaStream_t st);

@@ -78,7 +78,8 @@ static int get_encode_fn(EncodeTiledFn* out) {
 }
 
 namespace frs {
-// generic 2-D bf16 row-major [rows, cols] map with a (box_cols x box_rows) SWIZZLE_128B box
+// generic 2-D bf16 row-major [rows, cols] map with a (box_cols x box_rows) box; the swizzle span equals the
+// box's inner extent: 64 columns -> SWIZZLE_128B, 32 columns -> SWIZZLE_64B
 int abi_make_tmap_bf16(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
                        uint32_t box_rows) {
   EncodeTiledFn enc = nullptr;
@@ -88,8 +89,10 @@ int abi_make_tmap_bf16(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols,
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  if (box_cols != 64 && box_cols != 32) return set_err(FRS_E_INVALID, "tensor map box must be 32 or 64 columns wide");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(FRS_E_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
   return FRS_OK;
