@@ -109,22 +109,25 @@ class WordPiece:
             return cls([line.rstrip("\n") for line in f])
 
     def _word_ids(self, texts: list[str]) -> list[list[int]]:
-        return [e.ids for e in self._tk.encode_batch(list(texts), add_special_tokens=False)]
+        enc = self._tk.encode_batch_fast if hasattr(self._tk, "encode_batch_fast") else self._tk.encode_batch
+        return [e.ids for e in enc(list(texts), add_special_tokens=False)]
 
     def pack_texts(self, texts: list[str], max_len: int = MAX_LEN):
         """`[CLS] t [SEP]` per text, truncated to max_len.  Returns (ids int32 [total], cu_seqlens
-        int32 [n+1])."""
+        int32 [n+1]).  The Rust tokenizer runs on all host threads and releases the GIL; the packing
+        below is vectorised numpy (no per-token Python work)."""
         body = self._word_ids(texts)
-        lens = np.fromiter((min(len(b), max_len - 2) + 2 for b in body), dtype=np.int64, count=len(body))
-        cu = np.zeros(len(body) + 1, dtype=np.int32)
-        np.cumsum(lens, out=cu[1:])
+        n = len(body)
+        blen = np.fromiter((min(len(b), max_len - 2) for b in body), dtype=np.int64, count=n)
+        cu = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(blen + 2, out=cu[1:])
         ids = np.empty(int(cu[-1]), dtype=np.int32)
-        for i, b in enumerate(body):
-            o = cu[i]
-            n = lens[i] - 2
-            ids[o] = CLS
-            ids[o + 1:o + 1 + n] = b[:n]
-            ids[o + 1 + n] = SEP
+        ids[cu[:-1]] = CLS
+        ids[cu[1:] - 1] = SEP
+        if int(blen.sum()):
+            flat = np.concatenate([np.asarray(b[:k], dtype=np.int32) for b, k in zip(body, blen) if k])
+            pos = np.arange(flat.size, dtype=np.int64) + np.repeat(2 * np.arange(n, dtype=np.int64) + 1, blen)
+            ids[pos] = flat
         return ids, cu
 
     def pack_pairs(self, pairs: list, max_len: int = MAX_LEN):
