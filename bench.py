@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the retrieval hot path (BASELINE.json `metric`):
 QPS of exact top-15 cosine search over 10M x 384-d bf16 chunks, 32-query batches, on 1/2/4/8 B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload search|embed|rerank|pipeline]
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one 32-query batch searched over the whole corpus (10M rows in total, sharded over the
@@ -391,7 +391,17 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["search", "embed", "rerank", "pipeline"], default="search",
+                    help="search = the headline metric (default); the others are BASELINE.json configs[2] / configs[4], see bench_encoders.py")
     args = ap.parse_args()
+    if args.workload != "search":
+        import bench_encoders
+
+        if args.impl == "reference":
+            bench_encoders.run_reference(args)
+        else:
+            bench_encoders.run_ours(args, ClockSampler, summarize_clocks)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -157,6 +157,7 @@ class Embedder:
     sentence-transformers modules.json: Transformer -> Pooling(cls) -> Normalize)."""
 
     SYNTHETIC_SEED = 1234
+    PIPELINE_TEXTS = 512  # texts per tokenise/encode slice of a large encode() call
 
     def __init__(self, model: str | None = None, device: int = 0, pool: str = "cls", max_tokens: int = 65536,
                  tokenizer: WordPiece | None = None):
@@ -172,9 +173,24 @@ class Embedder:
         batch = [texts] if single else list(texts)
         if not batch:
             return np.zeros((0, self.bert.shape.hidden), dtype=np.float32)
-        ids, cu = self.tokenizer.pack_texts(batch)
-        out = self.bert.embed_packed(ids, cu, self.pool)
-        return out[0] if single else out
+        if len(batch) <= self.PIPELINE_TEXTS:
+            ids, cu = self.tokenizer.pack_texts(batch)
+            out = self.bert.embed_packed(ids, cu, self.pool)
+            return out[0] if single else out
+        # ingest-sized input (ingest.py:52-66 posts 64 chunks at a time; a drop-in caller can pass them
+        # all): the host tokenises slice i+1 (Rust, GIL released) while the GPU encodes slice i
+        from concurrent.futures import ThreadPoolExecutor
+
+        slices = [batch[s:s + self.PIPELINE_TEXTS] for s in range(0, len(batch), self.PIPELINE_TEXTS)]
+        outs = []
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            nxt = pool.submit(self.tokenizer.pack_texts, slices[0])
+            for i in range(len(slices)):
+                ids, cu = nxt.result()
+                if i + 1 < len(slices):
+                    nxt = pool.submit(self.tokenizer.pack_texts, slices[i + 1])
+                outs.append(self.bert.embed_packed(ids, cu, self.pool))
+        return np.concatenate(outs)
 
     def close(self) -> None:
         self.bert.close()

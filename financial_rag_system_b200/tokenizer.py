@@ -98,6 +98,8 @@ class WordPiece:
                                                    lowercase=True)
         tk.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
         self._tk = tk
+        self._cache: dict[str, np.ndarray] = {}
+        self.cache_entries = 262144
 
     @classmethod
     def synthetic(cls) -> "WordPiece":
@@ -111,6 +113,19 @@ class WordPiece:
     def _word_ids(self, texts: list[str]) -> list[list[int]]:
         enc = self._tk.encode_batch_fast if hasattr(self._tk, "encode_batch_fast") else self._tk.encode_batch
         return [e.ids for e in enc(list(texts), add_special_tokens=False)]
+
+    def _cached_ids(self, texts: list[str]) -> list[np.ndarray]:
+        """WordPiece ids (no specials) as int32 arrays, through a bounded text -> ids cache: the rerank
+        path sees the same chunk texts again and again (they come out of the chunk store), only the
+        query side is new."""
+        cache = self._cache
+        missing = [t for t in dict.fromkeys(texts) if t not in cache]
+        if missing:
+            if len(cache) + len(missing) > self.cache_entries:
+                cache.clear()
+            for t, ids in zip(missing, self._word_ids(missing)):
+                cache[t] = np.asarray(ids[:MAX_LEN], dtype=np.int32)
+        return [cache[t] for t in texts]
 
     def pack_texts(self, texts: list[str], max_len: int = MAX_LEN):
         """`[CLS] t [SEP]` per text, truncated to max_len.  Returns (ids int32 [total], cu_seqlens
@@ -132,31 +147,35 @@ class WordPiece:
 
     def pack_pairs(self, pairs: list, max_len: int = MAX_LEN):
         """`[CLS] a [SEP] b [SEP]` with token types 0/1; `longest_first` truncation as the Rust `tokenizers`
-        library implements it.
-        Returns (ids, type_ids, cu_seqlens)."""
-        a_ids = self._word_ids([p[0] for p in pairs])
-        b_ids = self._word_ids([p[1] for p in pairs])
-        seqs, types = [], []
-        for a, b in zip(a_ids, b_ids):
-            budget = max_len - 3
-            if len(a) + len(b) > budget:
-                # tokenizers' TruncationStrategy::LongestFirst (the fast tokenizer AutoTokenizer returns):
-                # only the longer side is cut while the shorter fits, else both go to budget/2 (+1 for
-                # the longer one when the budget is odd)
-                n1, n2, swap = len(a), len(b), False
-                if n1 > n2:
-                    n1, n2, swap = n2, n1, True
-                n2 = n1 if n1 > budget else max(n1, budget - n1)
-                if n1 + n2 > budget:
-                    n1 = budget // 2
-                    n2 = n1 + budget % 2
-                if swap:
-                    n1, n2 = n2, n1
-                a, b = a[:n1], b[:n2]
-            seqs.append([CLS] + a + [SEP] + b + [SEP])
-            types.append([0] * (len(a) + 2) + [1] * (len(b) + 1))
-        cu = np.zeros(len(seqs) + 1, dtype=np.int32)
-        np.cumsum([len(s) for s in seqs], out=cu[1:])
-        ids = np.fromiter((t for s in seqs for t in s), dtype=np.int32, count=int(cu[-1]))
-        tts = np.fromiter((t for s in types for t in s), dtype=np.int32, count=int(cu[-1]))
+        library implements it (TruncationStrategy::LongestFirst, what AutoTokenizer's fast tokenizer
+        does): only the longer side is cut while the shorter fits, else both go to budget/2 (+1 for the
+        longer one when the budget is odd).  Returns (ids, type_ids, cu_seqlens)."""
+        a_ids = self._cached_ids([p[0] for p in pairs])
+        b_ids = self._cached_ids([p[1] for p in pairs])
+        n = len(pairs)
+        budget = max_len - 3
+        la = np.fromiter((len(a) for a in a_ids), dtype=np.int64, count=n)
+        lb = np.fromiter((len(b) for b in b_ids), dtype=np.int64, count=n)
+        over = la + lb > budget
+        if over.any():
+            n1, n2 = np.minimum(la, lb), np.maximum(la, lb)
+            swap = la > lb
+            n2 = np.where(n1 > budget, n1, np.maximum(n1, budget - n1))
+            both = n1 + n2 > budget
+            n1 = np.where(both, budget // 2, n1)
+            n2 = np.where(both, budget // 2 + budget % 2, n2)
+            ta, tb = np.where(swap, n2, n1), np.where(swap, n1, n2)
+            la, lb = np.where(over, ta, la), np.where(over, tb, lb)
+        cu = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(la + lb + 3, out=cu[1:])
+        ids = np.empty(int(cu[-1]), dtype=np.int32)
+        tts = np.zeros(int(cu[-1]), dtype=np.int32)
+        for i in range(n):
+            o, x, y = int(cu[i]), int(la[i]), int(lb[i])
+            ids[o] = CLS
+            ids[o + 1:o + 1 + x] = a_ids[i][:x]
+            ids[o + 1 + x] = SEP
+            ids[o + 2 + x:o + 2 + x + y] = b_ids[i][:y]
+            ids[o + 2 + x + y] = SEP
+            tts[o + 2 + x:o + 3 + x + y] = 1
         return ids, tts, cu
