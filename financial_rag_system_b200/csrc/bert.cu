@@ -17,6 +17,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#ifndef FRS_BG_SLEEP_NS
+#define FRS_BG_SLEEP_NS 64
+#endif
 #include "bert.cuh"
 #include "common.cuh"
 
@@ -43,6 +46,15 @@ __device__ __noinline__ void trap_with_code(uint32_t code, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_c(uint64_t* bar, uint32_t parity, uint32_t code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) trap_with_code(code, parity);
+  }
+}
+// Same, for the single-thread producer / MMA-issuer roles: they share an SM sub-partition with two
+// softmax (or epilogue) warps, and a tight polling loop would take issue slots from them.
+__device__ __forceinline__ void mbar_wait_bg(uint64_t* bar, uint32_t parity, uint32_t code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(FRS_BG_SLEEP_NS);
     if (++spins > (1u << 22)) trap_with_code(code, parity);
   }
 }
@@ -517,20 +529,20 @@ constexpr int kAttnThreads = 384;
 constexpr int kAttnRegsLow = 64;
 constexpr int kAttnRegsHigh = 216;
 constexpr int kKB = 128;              // keys per block
-constexpr int kKVStages = 3;
+constexpr int kKVStages = 4;
 constexpr int kQBytes = kBM * 128;            // 128 queries x 64 dims
 constexpr int kKBytes = kKB * 128;            // 128 keys x 64 dims
 constexpr int kVSlab = 64 * 128;              // 64 dims x 64 keys
 constexpr int kVBytes = 2 * kVSlab;           // 128 keys
 constexpr int kKVBytes = kKBytes + kVBytes;
-constexpr int kPSlab = kBM * 128;             // 128 queries x 64 keys
-constexpr int kPBytes = 2 * kPSlab;           // per head
+constexpr int kTmemS = 0;                     // TMEM columns: S of head h at [128h, +128)
+constexpr int kTmemO = 256;                   //   O block of head h at [256 + 32h, +32)
+constexpr int kTmemP = 320;                   //   P of head h (bf16 pairs) at [320 + 64h, +64)
 
 struct AttnSmem {
   static constexpr int q = 0;                                  // [2]
   static constexpr int kv = q + 2 * kQBytes;                   // [kKVStages] K | Vt slab 0 | Vt slab 1
-  static constexpr int pp = kv + kKVStages * kKVBytes;         // [2 heads]
-  static constexpr int bars = pp + 2 * kPBytes;
+  static constexpr int bars = kv + kKVStages * kKVBytes;
   static constexpr int nbars = 2 + 2 + 2 * kKVStages + 8;
   static constexpr int holder = bars + nbars * 8;
   static constexpr int total = holder + 16;
@@ -578,7 +590,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder;
-  // TMEM columns: S of head h at [128h, 128h+128), O block of head h at [256+32h, +32)
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAttnRegsLow));
   if (warp == 0) {
@@ -591,13 +602,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const QBlock qb = p.qblk[item / kHeadPairs];
         const int hp = item % kHeadPairs;
         const uint32_t qbuf = li & 1;
-        mbar_wait_c(&q_empty[qbuf], ((li >> 1) & 1) ^ 1, 105u);
+        mbar_wait_bg(&q_empty[qbuf], ((li >> 1) & 1) ^ 1, 105u);
         mbar_arrive_expect_tx(&q_full[qbuf], kQBytes);
         tma_load_2d(sm + AttnSmem::q + qbuf * kQBytes, &tmap_qk, &q_full[qbuf], hp * 64, qb.q_tok0, kEvictNormal);
         const int nkb = (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const uint32_t stage = g % kKVStages;
-          mbar_wait_c(&kv_empty[stage], ((g / kKVStages) & 1) ^ 1, 106u);
+          mbar_wait_bg(&kv_empty[stage], ((g / kKVStages) & 1) ^ 1, 106u);
           mbar_arrive_expect_tx(&kv_full[stage], kKVBytes);
           uint8_t* dst = sm + AttnSmem::kv + (size_t)stage * kKVBytes;
           const int tok = qb.kv_tok0 + kb * kKB;
@@ -636,19 +647,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       };
       auto issue_scores = [&](const Cursor& c) {
         const uint32_t qbuf = c.li & 1;
-        if (c.kb == 0) mbar_wait_c(&q_full[qbuf], (c.li >> 1) & 1, 107u);
+        if (c.kb == 0) mbar_wait_bg(&q_full[qbuf], (c.li >> 1) & 1, 107u);
         const uint32_t stage = c.g % kKVStages;
-        mbar_wait_c(&kv_full[stage], (c.g / kKVStages) & 1, 108u);
+        mbar_wait_bg(&kv_full[stage], (c.g / kKVStages) & 1, 108u);
         const uint32_t q_addr = smem_u32(sm + AttnSmem::q + qbuf * kQBytes);
         const uint32_t k_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait_c(&s_free[h], (c.g & 1) ^ 1, 109u);  // softmax warps hold the previous S of this head in registers
+          mbar_wait_bg(&s_free[h], (c.g & 1) ^ 1, 109u);  // softmax warps hold the previous S of this head in registers
           tc_fence_after();
           const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
           const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
-          tc_mma<false>(tmem_base + 128 * h, da, db, idesc_s, 0u);
-          tc_mma<false>(tmem_base + 128 * h, da + 2, db + 2, idesc_s, 1u);
+          tc_mma<false>(tmem_base + kTmemS + 128 * h, da, db, idesc_s, 0u);
+          tc_mma<false>(tmem_base + kTmemS + 128 * h, da + 2, db + 2, idesc_s, 1u);
           tc_commit(&s_full[h]);
         }
       };
@@ -668,16 +679,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const uint32_t v_addr = smem_u32(sm + AttnSmem::kv + (size_t)stage * kKVBytes) + kKBytes;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait_c(&p_full[h], cp.g & 1, 110u);  // P of this block is in shared memory, previous O block was read
+          mbar_wait_bg(&p_full[h], cp.g & 1, 110u);  // P of this block is in tensor memory, previous O block was read
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(sm + AttnSmem::pp + h * kPBytes);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const uint64_t da = make_desc_sw128(p_addr + s * kPSlab);
             const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              tc_mma<false>(tmem_base + 256 + 32 * h, da + 2 * kk, db + 2 * kk, idesc_o, (uint32_t)((s | kk) != 0));
+            for (int kk = 0; kk < 4; ++kk)  // 16 keys per MMA = 8 columns of packed bf16 pairs
+              tc_mma_ts(tmem_base + kTmemO + 32 * h, tmem_base + kTmemP + 64 * h + (s * 4 + kk) * 8, db + 2 * kk, idesc_o,
+                        (uint32_t)((s | kk) != 0));
           }
           tc_commit(&o_full[h]);
         }
@@ -693,11 +703,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     const uint32_t quarter = warp & 3;
     const uint32_t h = (warp >> 2) - 1;
     const uint32_t row = quarter * 32 + lane;
-    const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + 128 * h;
-    const uint32_t t_o = tmem_base + ((quarter * 32u) << 16) + 256 + 32 * h;
-    uint8_t* prow = sm + AttnSmem::pp + h * kPBytes + row * 128;
-    const uint32_t sw = row & 7;
+    const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + kTmemS + 128 * h;
+    const uint32_t t_o = tmem_base + ((quarter * 32u) << 16) + kTmemO + 32 * h;
+    const uint32_t t_p = tmem_base + ((quarter * 32u) << 16) + kTmemP + 64 * h;
     uint32_t g = 0;
+    // -DFRS_ATTN_TIMING: per-phase clock sums of the softmax warps of CTA 0 (printed by launch_attention)
+#ifdef FRS_ATTN_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define FRS_T(i) do { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; } while (0)
+#else
+#define FRS_T(i) do { } while (0)
+#endif
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const QBlock qb = p.qblk[item / kHeadPairs];
       const int hp = item % kHeadPairs;
@@ -713,8 +729,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const int lo = kb == 0 ? key_off : 0;
         const int hi = min(kKB, key_off + qb.seq_len - kb * kKB);
         const bool full = lo == 0 && hi == kKB;
+        FRS_T(0);
         mbar_wait_c(&s_full[h], g & 1, 111u);
         tc_fence_after();
+        FRS_T(1);
         tmem_ld_32x32(t_s, s0);
         tmem_ld_32x32(t_s + 32, s1);
         tmem_ld_32x32(t_s + 64, s2);
@@ -724,6 +742,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[h]);
+        FRS_T(2);
         if (!full) {
           auto mask = [&](uint32_t(&sv)[32], int c) {
 #pragma unroll
@@ -746,10 +765,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         }
         const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
         const float alpha = ex2_approx(m - m_new);  // 0 on the first block (m = -inf)
+        FRS_T(3);
         if (kb > 0) {
           // previous P.V finished: its O block is ready and P may be overwritten
           mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
           tc_fence_after();
+          FRS_T(4);
           uint32_t ob[32];
           tmem_ld_32x32(t_o, ob);
           tmem_ld_wait();
@@ -758,34 +779,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           l *= alpha;
         }
         m = m_new;
-        // p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V); masked keys give 0
+        FRS_T(5);
+        // p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V); masked keys give 0.
+        // P goes straight back to tensor memory as the A operand of P.V: key k of this row = half (k & 1) of
+        // column k / 2.  It never touches shared memory.
         float ps0 = 0.f, ps1 = 0.f;
-        auto expo = [&](uint32_t(&sv)[32], int c) {
-          uint32_t pk[16];
+        uint32_t pw0[32], pw1[32];  // two buffers: the asynchronous TMEM store of the first may still read it
+        auto expo = [&](uint32_t(&sv)[32], uint32_t(&pw)[32], int half) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+#ifdef FRS_ATTN_NOEXP_H1  // measurement only: head 1 skips the MUFU (wrong results) to expose MUFU sharing
+            const float a = h ? (__uint_as_float(sv[2 * j]) - m) * 0.001f : ex2_approx(__uint_as_float(sv[2 * j]) - m);
+            const float b = h ? (__uint_as_float(sv[2 * j + 1]) - m) * 0.001f : ex2_approx(__uint_as_float(sv[2 * j + 1]) - m);
+#else
             const float a = ex2_approx(__uint_as_float(sv[2 * j]) - m);
             const float b = ex2_approx(__uint_as_float(sv[2 * j + 1]) - m);
+#endif
             ps0 += a;
             ps1 += b;
-            pk[j] = pack_bf16x2(a, b);
-          }
-          uint8_t* slab = prow + (c >> 1) * kPSlab;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = ((uint32_t)((c & 1) * 4 + j)) ^ sw;
-            *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            pw[half * 16 + j] = pack_bf16x2(a, b);
           }
         };
-        expo(s0, 0);
-        expo(s1, 1);
-        expo(s2, 2);
-        expo(s3, 3);
+        expo(s0, pw0, 0);
+        expo(s1, pw0, 1);
+        tmem_st_32x32(t_p, pw0);
+        expo(s2, pw1, 0);
+        expo(s3, pw1, 1);
+        tmem_st_32x32(t_p + 32, pw1);
         l += ps0 + ps1;
-        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[h]);
+        FRS_T(6);
       }
       // last O block, normalise, write the context rows of this head
       mbar_wait_c(&o_full[h], (g - 1) & 1, 113u);
@@ -807,7 +833,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       }
       // the O block of this item has been read: the next item's first P.V may overwrite it only after
       // this warp arrives on p_full again, which happens after this point (program order)
+      FRS_T(7);
     }
+#ifdef FRS_ATTN_TIMING
+    if (p.timing && lane == 0 && blockIdx.x == 0)
+      for (int i = 0; i < 8; ++i) p.timing[(warp - 4) * 8 + i] = tacc[i];
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -962,6 +993,24 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   const int items = p.nqb * kHeadPairs;
   if (items <= 0) return cudaSuccess;
   const int grid = items < sm_count ? items : sm_count;
+#ifdef FRS_ATTN_TIMING
+  static long long* th = nullptr;
+  static int calls = 0;
+  if (!th) cudaHostAlloc(&th, 64 * 8, cudaHostAllocMapped);
+  AttnParams pd = p;
+  cudaHostGetDevicePointer(&pd.timing, th, 0);
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, pd);
+  if (++calls % 12 == 0) {
+    cudaStreamSynchronize(st);
+    static const char* names[8] = {"loop", "wait_s", "ld_s", "max", "wait_o", "o_upd", "exp+store", "item_tail"};
+    for (int w = 0; w < 8; w += 4) {
+      fprintf(stderr, "[attn timing] CTA0 warp %d:", w + 4);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%lld", names[i], th[w * 8 + i]);
+      fprintf(stderr, "\n");
+    }
+  }
+  return cudaGetLastError();
+#endif
   attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, p);
   return cudaGetLastError();
 }

@@ -56,6 +56,7 @@ struct AttnParams {
   const QBlock* qblk;
   int nqb;             // work items = nqb * kHeadPairs
   __nv_bfloat16* ctx;  // [rows, 384]
+  long long* timing;   // -DFRS_ATTN_TIMING builds: [8 warps][8 phases] clock sums of CTA 0, else null
 };
 
 size_t gemm_smem_bytes(int epi);
