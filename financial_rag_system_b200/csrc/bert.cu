@@ -204,12 +204,12 @@ constexpr int kNSub = 192;  // N of one tcgen05.mma / rows of one weight TMA box
 
 template <int BN>
 struct GemmCfg {
-  static_assert(BN == 192 || BN == 384, "tile N is 192 or 384");
+  static_assert(BN == 192, "tile N is 192");
   static constexpr int kStageA = kBM * 128;    // 128 rows x 64 bf16
   static constexpr int kStageB = BN * 128;     // BN rows x 64 bf16
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN == 192 ? 4 : 2;
-  static constexpr int kAcc = BN == 192 ? 2 : 1;  // TMEM accumulator stages (2 x 192 or 1 x 384 columns)
+  static constexpr int kStages = 4;
+  static constexpr int kAcc = 2;  // TMEM accumulator stages (2 x 192 columns): epilogue(i) overlaps MMA(i+1)
   static constexpr int kNSplit = BN / kNSub;
   static constexpr int kColsPerThread = BN / 2;   // two epilogue warps share a TMEM lane quarter
   static constexpr int kRing = kStages * kStage;
@@ -217,9 +217,9 @@ struct GemmCfg {
   static constexpr int kOutBytes = kBM * kNSub * 2;    // 48 KB: 128 x 192 bf16
   static constexpr int kOutBufs = 1;  // (a second buffer costs a ring stage and measured slower)
   static constexpr int kParF = kOut + kOutBufs * kOutBytes;  // fp32 params: bias[1536] | gamma[384] | beta[384]
-  static constexpr int kStat = kParF + (1536 + 768) * 4;  // float2 [2 parity][2 halves][128 rows] (ResLN only)
-  static constexpr int kBars = kStat + (BN == 384 ? 2 * 2 * 128 * 8 : 0);
-  static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc) * 8;
+  static constexpr int kStat = kParF + (1536 + 768) * 4;  // ResLN: float2 [2 parity][4 partials][128 rows]
+  static constexpr int kBars = kStat + 2 * 4 * 128 * 8;
+  static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc + 2) * 8;
   static constexpr int kTotal = kHolder + 16;
 };
 
@@ -228,6 +228,11 @@ struct GemmCfg {
 // full 128-byte lines.)  Named barriers 2 / 3 = "staging is free" / "staging is written".
 constexpr uint32_t kBarStageFree = 2, kBarStageFull = 3;
 
+// ResLN (bias + residual + LayerNorm over the 384-wide row) runs on a CLUSTER OF TWO CTAs: each CTA owns
+// one 192-column half of the same 128-row tile — the same 2-accumulator pipeline as the other GEMMs, so
+// the epilogue overlaps the next tile's MMAs (a 384-column accumulator cannot be double-buffered in 512
+// TMEM columns).  The halves exchange their per-row (sum, sum of squares) through distributed shared
+// memory: every epilogue thread stores its partial into the peer CTA and arrives on the peer's mbarrier.
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -246,13 +251,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty = full + C::kStages;
   uint64_t* tfull = empty + C::kStages;
   uint64_t* tempty = tfull + C::kAcc;
+  uint64_t* xbar = tempty + C::kAcc;  // ResLN: the peer's partial statistics of tile parity 0 / 1 have landed
   uint32_t* holder = reinterpret_cast<uint32_t*>(sm + C::kHolder);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  const int nt_count = p.N / BN;
+  constexpr bool kPair = EPI == kEpiResLN;  // 2-CTA cluster, one column half each
+  const int nt_count = kPair ? 1 : p.N / BN;
   const int ksteps = p.K / 64;
   const int num_tiles = p.num_mtiles * nt_count;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
+  const int tile0 = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)num_clusters_x() : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -263,6 +273,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kGemmEpiWarps);
     }
+    mbar_init(&xbar[0], kGemmEpiThreads);  // one arrive per epilogue thread of the peer CTA
+    mbar_init(&xbar[1], kGemmEpiThreads);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
@@ -279,6 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (kPair) cluster_sync_all();  // the peer's mbarriers exist before anybody arrives on them
   const uint32_t tmem_base = *holder;
 
   if (warp == 0) {
@@ -287,8 +300,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / nt_count, nt = tile % nt_count;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -308,7 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(1u, kBM, kNSub);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
         const uint32_t acc = lt % C::kAcc;
         const uint32_t aph = (lt / C::kAcc) & 1;
         mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
@@ -344,8 +357,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
     }
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int mt = tile / nt_count, nt = tile % nt_count;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
+      const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
       const uint32_t acc = lt % C::kAcc;
       const uint32_t aph = (lt / C::kAcc) & 1;
       const int grow = mt * kBM + (int)row;
@@ -354,7 +367,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // their global-memory latency hides behind the tile's MMA main loop
       uint4 rres[EPI == kEpiResLN ? C::kColsPerThread / 8 : 1];
       if constexpr (EPI == kEpiResLN) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)grow * kHid + half * C::kColsPerThread);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)grow * kHid + nt * BN + half * C::kColsPerThread);
 #pragma unroll
         for (int j = 0; j < C::kColsPerThread / 8; ++j) rres[j] = live ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
@@ -434,11 +447,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tma_store_commit();
         }
       } else {
-        // bias + residual, row statistics; the pre-LayerNorm value goes back to TMEM (fp32)
+        // bias + residual, row statistics of this CTA's 192 columns; the pre-LayerNorm value goes back to
+        // TMEM (fp32)
         float sum = 0.f, sq = 0.f;
 #pragma unroll
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
-          const int col = (int)half * C::kColsPerThread + c * 32;
+          const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           const uint32_t rw[16] = {rres[4 * c].x,     rres[4 * c].y,     rres[4 * c].z,     rres[4 * c].w,
@@ -458,53 +472,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_st_32x32(taddr + c * 32, v);
         }
         tmem_st_wait();
-        float2* st = sstat + (lt & 1) * 256;
+        // partial statistics: slots {0,1} = this CTA's column quarters, {2,3} = the peer's (written by the
+        // peer through distributed shared memory).  Double-buffered by tile parity.
+        const uint32_t par = lt & 1;
+        float2* st = sstat + par * 512;
         st[half * 128 + row] = make_float2(sum, sq);
+        st_cluster_f32x2(mapa_u32(smem_u32(st + (2 + half) * 128 + row), crank ^ 1u), sum, sq);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&xbar[par]), crank ^ 1u));
         named_bar_sync(1, kGemmEpiThreads);
-        const float2 other = st[(half ^ 1) * 128 + row];
-        const float mean = (sum + other.x) * (1.0f / kHid);
-        const float var = fmaxf((sq + other.y) * (1.0f / kHid) - mean * mean, 0.f);
+        {
+          uint32_t spins = 0;
+          while (!mbar_try_wait_cluster(&xbar[par], (lt >> 1) & 1)) {
+            if (++spins > (1u << 22)) trap_with_code(120u, (lt >> 1) & 1);
+          }
+        }
+        const float2 s0 = st[row], s1 = st[128 + row], s2 = st[256 + row], s3 = st[384 + row];
+        // (local + local) + (peer + peer): the same two sums in both CTAs, so both see identical statistics
+        const float tsum = (s0.x + s1.x) + (s2.x + s3.x);
+        const float tsq = (s0.y + s1.y) + (s2.y + s3.y);
+        const float mean = tsum * (1.0f / kHid);
+        const float var = fmaxf(tsq * (1.0f / kHid) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
-        // normalise and store in two rounds of 3 column chunks: staging boxes [128 rows][32 columns],
-        // SWIZZLE_64B, box (half, chunk % 3)
-        uint8_t* sout = sout0;
+        if (issuer) tma_store_wait_read<0>();  // the previous tile's stores have read the staging tile
+        named_bar_sync(kBarStageFree, kGemmEpiThreads);
 #pragma unroll 1
-        for (int round = 0; round < 2; ++round) {
-          if (issuer) tma_store_wait_read<0>();
-          named_bar_sync(kBarStageFree, kGemmEpiThreads);
-#pragma unroll 1
-          for (int cc = 0; cc < 3; ++cc) {
-            const int c = round * 3 + cc;
-            const int col = (int)half * C::kColsPerThread + c * 32;
-            tmem_ld_32x32(taddr + c * 32, v);
-            tmem_ld_wait();
-            if (c == C::kColsPerThread / 32 - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[acc]);
-            }
-            uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * sgamma[col + 2 * j] + sbeta[col + 2 * j];
-              const float b =
-                  (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
-              o[j] = pack_bf16x2(a, b);
-            }
-            uint8_t* box = sout + (half * 3 + cc) * 8192 + row * 64;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(box + ((j ^ ((row >> 1) & 3)) << 4)) =
-                  make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int c = 0; c < C::kColsPerThread / 32; ++c) {
+          const int ct = (int)half * C::kColsPerThread + c * 32;  // column within this CTA's tile
+          const int col = nt * BN + ct;
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          fence_proxy_async();
-          named_bar_sync(kBarStageFull, kGemmEpiThreads);
-          if (issuer) {
+          uint32_t o[16];
 #pragma unroll
-            for (int b = 0; b < 6; ++b)
-              tma_store_2d(&tmap_out, sout + b * 8192, (b / 3) * C::kColsPerThread + (round * 3 + b % 3) * 32, mt * kBM);
-            tma_store_commit();
+          for (int j = 0; j < 16; ++j) {
+            const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * sgamma[col + 2 * j] + sbeta[col + 2 * j];
+            const float b =
+                (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
+            o[j] = pack_bf16x2(a, b);
           }
+          uint8_t* box = sout0 + (ct >> 6) * 16384 + row * 128;  // [128 rows][64 columns], SWIZZLE_128B
+          const uint32_t j0 = (uint32_t)(ct & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(box + (((j0 + j) ^ (row & 7)) << 4)) =
+                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        fence_proxy_async();
+        named_bar_sync(kBarStageFull, kGemmEpiThreads);
+        if (issuer) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) tma_store_2d(&tmap_out, sout0 + b * 16384, nt * BN + b * 64, mt * kBM);
+          tma_store_commit();
         }
       }
     }
@@ -512,6 +534,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer may still be writing into this CTA's shared memory
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -928,7 +951,8 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, __n
 // launchers
 // ---------------------------------------------------------------------------------------------
 size_t gemm_smem_bytes(int epi) {
-  return (epi == kEpiResLN ? GemmCfg<384>::kTotal : GemmCfg<192>::kTotal) + 1024;
+  (void)epi;
+  return GemmCfg<192>::kTotal + 1024;
 }
 size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
 
@@ -960,12 +984,31 @@ static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUte
     configured = true;
   }
   if (p.N % BN != 0 || p.K % 64 != 0 || p.N > 1536) return cudaErrorInvalidValue;
-  const int tiles = p.num_mtiles * (p.N / BN);
-  if (tiles <= 0) return cudaSuccess;
-  const int grid = tiles < sm_count ? tiles : sm_count;
   GemmParams pd = p;
   static const int dbg = getenv("FRS_GEMM_DEBUG") ? atoi(getenv("FRS_GEMM_DEBUG")) : 0;
   pd.debug = dbg;
+  if constexpr (EPI == kEpiResLN) {
+    // one cluster of two CTAs per 128-row tile (column halves), persistent over the row tiles
+    if (p.N != 2 * BN) return cudaErrorInvalidValue;
+    if (p.num_mtiles <= 0) return cudaSuccess;
+    const int clusters = p.num_mtiles < sm_count / 2 ? p.num_mtiles : sm_count / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI>, ta, tb, to, to2, pd);
+  }
+  const int tiles = p.num_mtiles * (p.N / BN);
+  if (tiles <= 0) return cudaSuccess;
+  const int grid = tiles < sm_count ? tiles : sm_count;
   gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, to, to2, pd);
   return cudaGetLastError();
 }
@@ -976,7 +1019,7 @@ cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const 
   switch (epi) {
     case kEpiQKV: return launch_gemm_t<192, kEpiQKV>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
     case kEpiGelu: return launch_gemm_t<192, kEpiGelu>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
-    case kEpiResLN: return launch_gemm_t<384, kEpiResLN>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
+    case kEpiResLN: return launch_gemm_t<192, kEpiResLN>(sm_count, tmap_a, tmap_b, tmap_out, tmap_out2, p, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -59,7 +59,6 @@ struct frs_encoder {
   int32_t *d_cu = nullptr, *d_rs = nullptr;  // caller cu_seqlens | internal row starts (multiples of 8)
   QBlock* d_qblk = nullptr;
   CUtensorMap t_x0, t_x1, t_ctx, t_h, t_qk, t_vt;  // box 64 x 128 (vt: 64 x 64): GEMM A operands, attention loads, stores
-  CUtensorMap t_x0_st, t_x1_st;                    // box 32 x 128, SWIZZLE_64B: LayerNorm epilogue stores
   // staging
   int32_t *h_cu = nullptr, *h_rs = nullptr, *h_ids = nullptr, *h_type = nullptr;
   QBlock* h_qblk = nullptr;
@@ -249,8 +248,6 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   EN_RC(abi_make_tmap_bf16(&e->t_h, e->h, T, kFfn, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_qk, e->qk, T, 2 * kHid, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_vt, e->vt, kHid, T, 64, 64));
-  EN_RC(abi_make_tmap_bf16(&e->t_x0_st, e->x0, T, kHid, 32, kBM));
-  EN_RC(abi_make_tmap_bf16(&e->t_x1_st, e->x1, T, kHid, 32, kBM));
 #undef EN_TRY
 #undef EN_RC
   *out = e;
@@ -360,7 +357,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x0;
     g.gamma = L.ln1g;
     g.beta = L.ln1b;
-    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_ctx, L.t_wo, e->t_x1_st, e->t_x1_st, g, st));
+    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_ctx, L.t_wo, e->t_x1, e->t_x1, g, st));
     if ((rc = prof_mark(e, kPOut, st))) return rc;
     // FFN
     g.N = kFfn;
@@ -374,7 +371,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x1;
     g.gamma = L.ln2g;
     g.beta = L.ln2b;
-    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->t_x0_st, e->t_x0_st, g, st));
+    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->t_x0, e->t_x0, g, st));
     if ((rc = prof_mark(e, kPDown, st))) return rc;
   }
   e->last_tokens = host_cu[n_seqs];
