@@ -167,6 +167,60 @@ class Collection:
             ids[s:e], scores[s:e] = self.index.search(q[s:e], code[s:e], mask[s:e], limit)
         return ids, scores
 
+    # -- persistence (the Qdrant volume of docker-compose.yml:26-27) ----------------------------------
+    def save(self, path: str, chunk_rows: int = 1 << 20) -> None:
+        """Write the collection to a directory: `rows.bin` (storage-dtype rows as they sit in HBM),
+        `codes.npy`, `points.jsonl` (id + payload per row) and `meta.json` (dtype, dictionaries)."""
+        import json
+        import os
+
+        os.makedirs(path, exist_ok=True)
+        with self._lock:
+            n = len(self.ids)
+            codes = np.empty(n, dtype=np.uint32)
+            with open(os.path.join(path, "rows.bin"), "wb") as f:
+                for s in range(0, n, chunk_rows):
+                    rows, c = self.index.export_raw(s, min(chunk_rows, n - s))
+                    rows.tofile(f)
+                    codes[s:s + len(c)] = c
+            np.save(os.path.join(path, "codes.npy"), codes)
+            with open(os.path.join(path, "points.jsonl"), "w") as f:
+                for pid, payload in zip(self.ids, self.payloads):
+                    f.write(json.dumps({"id": pid, "payload": payload}) + "\n")
+            with open(os.path.join(path, "meta.json"), "w") as f:
+                json.dump({"format": 1, "dtype": getattr(self.index, "dtype", "bf16"), "rows": n, "dim": FRS_DIM,
+                           "tickers": self._tickers, "doctypes": self._doctypes}, f)
+
+    @classmethod
+    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0, index=None, chunk_rows: int = 1 << 20):
+        """Rebuild a collection saved by `save`; every query then returns bit-identical ids and scores."""
+        import json
+        import os
+
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        n = int(meta["rows"])
+        c = cls(max(int(capacity or 0), n, 1), dtype=meta["dtype"], device=device, index=index)
+        codes = np.load(os.path.join(path, "codes.npy"))
+        esz, dt = (4, np.float32) if meta["dtype"] == "f32" else (2, np.uint16)
+        with open(os.path.join(path, "rows.bin"), "rb") as f:
+            for s in range(0, n, chunk_rows):
+                m = min(chunk_rows, n - s)
+                rows = np.frombuffer(f.read(m * FRS_DIM * esz), dtype=dt).reshape(m, FRS_DIM)
+                c.index.import_raw(rows, codes[s:s + m])
+        with open(os.path.join(path, "points.jsonl")) as f:
+            for row, line in enumerate(f):
+                rec = json.loads(line)
+                pid = rec["id"]
+                c.ids.append(pid)
+                c.payloads.append(rec["payload"])
+                if not int(codes[row]) & CODE_TOMBSTONE:
+                    c._row_of_id[pid] = row
+        c._codes = codes.astype(np.uint32)
+        c._tickers = {k: int(v) for k, v in meta["tickers"].items()}
+        c._doctypes = {k: int(v) for k, v in meta["doctypes"].items()}
+        return c
+
     def close(self) -> None:
         if hasattr(self.index, "close"):
             self.index.close()

@@ -407,6 +407,37 @@ extern "C" int frs_index_read_rows_host(frs_index* idx, int64_t row0, int64_t n,
 }
 
 // ---------------------------------------------------------------------------------------------
+// persistence: raw storage rows + payload codes
+// ---------------------------------------------------------------------------------------------
+extern "C" int frs_index_export_raw(frs_index* idx, int64_t row0, int64_t n, void* host_rows, uint32_t* host_codes) {
+  if (!idx || n < 0 || row0 < 0 || row0 + n > idx->size || (n > 0 && (!host_rows || !host_codes)))
+    return set_err(FRS_E_INVALID, "bad argument");
+  if (n == 0) return FRS_OK;
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  CU_TRY(cudaStreamSynchronize(idx->stream));
+  CU_TRY(cudaMemcpy(host_rows, (const char*)idx->rows + (size_t)row0 * idx->row_bytes(), (size_t)n * idx->row_bytes(),
+                    cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(host_codes, idx->codes + row0, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return FRS_OK;
+}
+
+extern "C" int frs_index_import_raw(frs_index* idx, const void* host_rows, const uint32_t* host_codes, int64_t n) {
+  if (!idx || n < 0 || (n > 0 && (!host_rows || !host_codes))) return set_err(FRS_E_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (idx->size + n > idx->capacity)
+    return set_err(FRS_E_CAPACITY, "index full: size %lld + %lld > capacity %lld", (long long)idx->size, (long long)n,
+                   (long long)idx->capacity);
+  if (n == 0) return FRS_OK;
+  CU_TRY(cudaSetDevice(idx->device));
+  CU_TRY(cudaMemcpy((char*)idx->rows + (size_t)idx->size * idx->row_bytes(), host_rows, (size_t)n * idx->row_bytes(),
+                    cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(idx->codes + idx->size, host_codes, (size_t)n * 4, cudaMemcpyHostToDevice));
+  idx->size += n;
+  return FRS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
 static int scan_grid(const frs_index* ix, uint32_t num_tiles) {

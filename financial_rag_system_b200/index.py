@@ -101,6 +101,24 @@ class VectorIndex:
         check(self._lib.frs_index_read_rows(self._h, int(row0), int(n), _ptr(out), _stream_ptr(self.device)))
         return out
 
+    # -- persistence ----------------------------------------------------------------------------
+    def export_raw(self, row0: int = 0, n: int | None = None):
+        """Stored rows exactly as they sit in HBM (uint16 bf16 bit patterns or float32) + payload codes."""
+        n = len(self) - row0 if n is None else n
+        rows = np.empty((n, FRS_DIM), dtype=np.float32 if self.dtype == "f32" else np.uint16)
+        codes = np.empty((n,), dtype=np.uint32)
+        check(self._lib.frs_index_export_raw(self._h, int(row0), int(n), _ptr(rows), _ptr(codes)))
+        return rows, codes
+
+    def import_raw(self, rows: np.ndarray, codes: np.ndarray) -> None:
+        """Append rows previously produced by export_raw (no normalisation, no rounding)."""
+        want = np.float32 if self.dtype == "f32" else np.uint16
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype != want or rows.ndim != 2 or rows.shape[1] != FRS_DIM:
+            raise ValueError(f"raw rows must be [n, 384] {np.dtype(want).name} for a {self.dtype} index")
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        check(self._lib.frs_index_import_raw(self._h, _ptr(rows), _ptr(codes), rows.shape[0]))
+
     def set_scan_grid(self, grid: int) -> None:
         check(self._lib.frs_index_set_scan_grid(self._h, int(grid)))
 

@@ -110,6 +110,13 @@ uint32_t* frs_index_codes_ptr(frs_index* idx);
 /* declare that rows [0, n) were filled in place through frs_index_rows_ptr() */
 int frs_index_set_size(frs_index* idx, int64_t n);
 
+/* Persistence (the role of the Qdrant volume, docker-compose.yml:26-27): the stored rows exactly as
+ * they sit in HBM (storage dtype, already normalised) and their payload codes.  export copies rows
+ * [row0, row0+n) to host memory (n * 384 * (2|4) bytes, n * 4 bytes); import appends n such rows
+ * without touching them, so a reloaded index answers every query bit-identically. */
+int frs_index_export_raw(frs_index* idx, int64_t row0, int64_t n, void* host_rows, uint32_t* host_codes);
+int frs_index_import_raw(frs_index* idx, const void* host_rows, const uint32_t* host_codes, int64_t n);
+
 /* qdrant.query_points(query=vec, limit=k, query_filter=Filter(must=[...]))
  * main.py:215-239, main2.py:160-163 — exact cosine top-k with payload filter.
  *   queries      [nq, 384] fp32, nq <= FRS_MAX_BATCH (need not be normalised)

@@ -29,6 +29,22 @@ class OracleIndex:
         ids, sc = so.exact_topk(self.rows, so.prepare_queries(q, "f32"), self.codes, code, mask, k)
         return ids, sc.astype(np.float32)
 
+    dtype = "f32"
+
+    def set_rows(self, row0, vecs, codes=None):
+        v = so.store_rows(vecs.cpu().numpy(), "f32")
+        self.rows[row0:row0 + len(v)] = v
+        if codes is not None:
+            self.codes[row0:row0 + len(v)] = codes.cpu().numpy().astype(np.int64).astype(np.uint32)
+
+    def export_raw(self, row0=0, n=None):
+        n = len(self.rows) - row0 if n is None else n
+        return self.rows[row0:row0 + n].copy(), self.codes[row0:row0 + n].copy()
+
+    def import_raw(self, rows, codes):
+        self.rows = np.concatenate([self.rows, np.asarray(rows, dtype=np.float32)])
+        self.codes = np.concatenate([self.codes, np.asarray(codes, dtype=np.uint32)])
+
 
 def _collection(n=400, seed=0):
     rng = np.random.default_rng(seed)
@@ -183,3 +199,19 @@ def test_dynamic_batcher_batches_search_and_rerank_too():
     assert r.embedder.calls == 2 and r.reranker.calls == 2
     direct = r.retrieve_batch(qs[:1], ts[:1], top_k=3)
     assert [h.row for h in res[0]] == [h.row for h in direct[0]]
+
+
+def test_save_and_load_round_trip(tmp_path):
+    c, ids, vecs, payloads = _collection(120)
+    t = payloads[5]["ticker"]
+    before = c.search(vecs[:8], t, limit=10)
+    c.save(str(tmp_path / "col"))
+    d = Collection.load(str(tmp_path / "col"), index=OracleIndex(0))
+    assert len(d) == len(c) and d.ids == c.ids and d.payloads == c.payloads
+    after = d.search(vecs[:8], t, limit=10)
+    assert np.array_equal(before[0], after[0]) and np.array_equal(before[1], after[1])
+    # the dictionaries survive: a new upsert with a known ticker gets the same code, ids stay idempotent
+    d.upsert([ids[0]], vecs[3:4], [payloads[0]])  # overwrite in place: row 0 now holds vector 3
+    assert len(d) == len(c)
+    got, sc = d.search(vecs[3:4], payloads[0]["ticker"], limit=2)
+    assert got[0, 0] == 0 and abs(sc[0, 0] - 1.0) < 1e-6

@@ -350,3 +350,33 @@ def test_full_size_properties_1m(dtype):
     assert np.array_equal(ids15[:4], oi)
     assert np.allclose(sc15[:4], os_, atol=SCORE_ATOL)
     ix.close()
+
+
+def test_export_import_raw_round_trip_is_bit_exact():
+    """Persistence: rows exported as they sit in HBM and imported into a fresh index answer every
+    query with identical ids and identical score bits (both storage dtypes)."""
+    from financial_rag_system_b200.index import VectorIndex
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, nq, k = 30000, 32, 15
+    x = torch.randn((n, 384), generator=g, device="cuda")
+    codes = torch.randint(0, 9, (n,), generator=g, device="cuda", dtype=torch.int32)
+    q = x[:nq] + 0.05 * torch.randn((nq, 384), generator=g, device="cuda")
+    qc = codes[:nq].clone()
+    qm = torch.full((nq,), 0x80FFFFFF - (1 << 32), dtype=torch.int64).to(torch.int32).cuda()
+    for dtype in ("bf16", "f32"):
+        a = VectorIndex(n, dtype=dtype, device=0)
+        a.add(x, codes)
+        ids_a, s_a = a.search(q, qc, qm, k)
+        rows, c = a.export_raw()
+        assert rows.shape == (n, 384) and rows.dtype == (np.uint16 if dtype == "bf16" else np.float32)
+        b = VectorIndex(n, dtype=dtype, device=0)
+        b.import_raw(rows[:10000], c[:10000])
+        b.import_raw(rows[10000:], c[10000:])
+        ids_b, s_b = b.search(q, qc, qm, k)
+        torch.cuda.synchronize()
+        assert torch.equal(ids_a, ids_b) and torch.equal(s_a, s_b)
+        with pytest.raises(ValueError):
+            b.import_raw(rows.astype(np.float64), c)
+        a.close()
+        b.close()
