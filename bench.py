@@ -238,9 +238,16 @@ def run_ours(args):
     gen_rows = torch.Generator(device=dev).manual_seed(1000 + rank)
     first_rows = first_codes = None
     chunk = 1 << 18
+    grouped = args.workload == "search_segmented"  # rows ingested ticker by ticker (ingest.py:109-177)
+    if grouped and world > 1:
+        raise SystemExit("--workload search_segmented is a single-GPU measurement")
+    cum = torch.cumsum(torch.tensor(zipf_probs() * TOTAL_ROWS, dtype=torch.float64, device=dev), 0)
     for s in range(0, length, chunk):
         m = min(chunk, length - s)
         x, codes = gen_chunk_cuda(torch, gen_rows, cent, probs_t, m)
+        if grouped:
+            rows_g = torch.arange(start + s, start + s + m, device=dev, dtype=torch.float64)
+            codes = torch.searchsorted(cum, rows_g, right=True).clamp_(max=N_TICKERS - 1).to(torch.int32)
         ix.add(x, codes)
         if s == 0 and rank == 0:
             first_rows, first_codes = x[:NQ].clone(), codes[:NQ].clone()
@@ -256,8 +263,20 @@ def run_ours(args):
         dist.broadcast(qc, 0)
     qm = torch.full((NQ,), TICKER_MASK - (1 << 32), dtype=torch.int64).to(torch.int32).to(dev)
     sh = ShardedIndex(ix, rank, world) if world > 1 else None
+    tiles_dev, n_tiles_total = None, (length + 127) // 128
+    if grouped:
+        # the tiles that hold rows of the batch's tickers (what Collection._batch_tiles computes on the host)
+        cum_h = np.concatenate([[0.0], cum.cpu().numpy()])
+        sets = [np.arange(int(cum_h[int(c)]) // 128, min(int(np.ceil(cum_h[int(c) + 1])), length - 1) // 128 + 1)
+                for c in np.unique(qc.cpu().numpy())]
+        tiles_dev = torch.from_numpy(np.unique(np.concatenate(sets)).astype(np.int32)).to(dev)
+        full_ids, _ = ix.search(q, qc, qm, K)
+        seg_ids, _ = ix.search_tiles(q, qc, qm, K, tiles_dev)
+        assert torch.equal(full_ids, seg_ids), "restricted scan must return the ids of the full scan"
 
     def step():
+        if tiles_dev is not None:
+            return ix.search_tiles(q, qc, qm, K, tiles_dev)
         if sh is None:
             return ix.search(q, qc, qm, K)
         return sh.search_async(q, qc, qm, K)
@@ -350,7 +369,7 @@ def run_ours(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        alg_bytes = length * (DIM * 2 + 4)
+        alg_bytes = (int(tiles_dev.numel()) * 128 if grouped else length) * (DIM * 2 + 4)
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
@@ -367,7 +386,8 @@ def run_ours(args):
             "value": NQ * args.steps / (ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world), **({"layout": f"rows grouped by ticker (ingest order); the batch's {int(np.unique(qc.cpu().numpy()).size)} "
+                                                             f"tickers occupy {int(tiles_dev.numel())} of {n_tiles_total} tiles; e2e is the full-scan host entry point"} if grouped else {})),
             "e2e": {"value": NQ * e2e_steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": NQ * DIM * 4 + 2 * NQ * 4, "d2h_bytes_per_step": NQ * K * (4 + 8)},
             "gpu_launches": launches_per_step * args.steps,
@@ -391,10 +411,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["search", "embed", "rerank", "pipeline"], default="search",
+    ap.add_argument("--workload", choices=["search", "search_segmented", "embed", "rerank", "pipeline"], default="search",
                     help="search = the headline metric (default); the others are BASELINE.json configs[2] / configs[4], see bench_encoders.py")
     args = ap.parse_args()
-    if args.workload != "search":
+    if args.workload not in ("search", "search_segmented"):
         import bench_encoders
 
         if args.impl == "reference":

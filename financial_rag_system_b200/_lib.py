@@ -50,6 +50,7 @@ PROTOTYPES = {
     "frs_index_export_raw": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "frs_index_import_raw": (_int, [_vp, _vp, _vp, _i64]),
     "frs_index_search": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
+    "frs_index_search_tiles": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _vp, _vp, _vp]),
     "frs_index_search_host": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "frs_index_search_local": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "frs_merge_shards": (_int, [_int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),

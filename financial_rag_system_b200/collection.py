@@ -41,6 +41,11 @@ class Collection:
         self.payloads: list[dict] = []
         self._codes = np.zeros(0, dtype=np.uint32)
         self._lock = threading.Lock()
+        # ticker-segmented search: the 128-row tiles that hold rows of each ticker.  Ingest is
+        # per ticker (ingest.py:109-177), so these sets are small and a filtered batch scans only them.
+        self.segmented = hasattr(index, "search_tiles")
+        self._ticker_tiles: dict[int, np.ndarray] = {}
+        self.last_scan_tiles = None  # (tiles scanned, tiles in the index) of the most recent search
 
     def __len__(self) -> int:
         return len(self.ids)
@@ -118,12 +123,25 @@ class Collection:
                     self._row_of_id[ids[i]] = len(self.ids)
                     self.ids.append(ids[i])
                     self.payloads.append(dict(payloads[i]))
+                self._note_tiles(len(self._codes), codes)
                 self._codes = np.concatenate([self._codes, codes])
             for i, row in upd:
                 code = np.array([self._row_code(payloads[i])], dtype=np.uint32)
                 self._set_row(row, vectors[i:i + 1], code)
                 self.payloads[row] = dict(payloads[i])
                 self._codes[row] = code[0]
+                self._note_tiles(row, code)
+
+    def _note_tiles(self, row0: int, codes: np.ndarray) -> None:
+        """Record which 128-row tiles now hold rows of which ticker (sets only ever grow: a stale entry
+        costs a little bandwidth, never correctness — rows are still filtered by the predicate)."""
+        tick = (codes & CODE_TICKER_MASK).astype(np.int64)
+        tile = (row0 + np.arange(len(codes), dtype=np.int64)) // 128
+        pairs = np.unique((tick << 32) | tile)
+        for t in np.unique(pairs >> 32):
+            new = (pairs[(pairs >> 32) == t] & 0xFFFFFFFF).astype(np.int64)
+            old = self._ticker_tiles.get(int(t))
+            self._ticker_tiles[int(t)] = new if old is None else np.union1d(old, new)
 
     def _set_row(self, row: int, vec: np.ndarray, code: np.ndarray) -> None:
         import torch
@@ -162,10 +180,33 @@ class Collection:
         mask = np.array([p[1] for p in pred], dtype=np.uint32)
         ids = np.empty((B, limit), dtype=np.int64)
         scores = np.empty((B, limit), dtype=np.float32)
+        total_tiles = (len(self._codes) + 127) // 128
         for s in range(0, B, FRS_MAX_BATCH):
             e = min(B, s + FRS_MAX_BATCH)
-            ids[s:e], scores[s:e] = self.index.search(q[s:e], code[s:e], mask[s:e], limit)
+            tiles = self._batch_tiles(code[s:e], mask[s:e], total_tiles) if self.segmented else None
+            if tiles is None:
+                self.last_scan_tiles = (total_tiles, total_tiles)
+                ids[s:e], scores[s:e] = self.index.search(q[s:e], code[s:e], mask[s:e], limit)
+            else:
+                self.last_scan_tiles = (len(tiles), total_tiles)
+                i_, s_ = self.index.search_tiles(q[s:e], code[s:e], mask[s:e], limit, tiles)
+                ids[s:e], scores[s:e] = i_.cpu().numpy(), s_.cpu().numpy()
         return ids, scores
+
+    def _batch_tiles(self, code: np.ndarray, mask: np.ndarray, total_tiles: int):
+        """Tiles a filtered batch has to read: the union of its tickers' tile sets; None = full scan (a
+        query without ticker condition, or a union that is most of the index anyway)."""
+        sets = []
+        for c, m in zip(code, mask):
+            if int(c) & CODE_TOMBSTONE:      # unknown keyword: matches nothing, needs no tile
+                continue
+            if (int(m) & CODE_TICKER_MASK) != CODE_TICKER_MASK:
+                return None
+            t = self._ticker_tiles.get(int(c) & CODE_TICKER_MASK)
+            if t is not None:
+                sets.append(t)
+        tiles = np.unique(np.concatenate(sets)) if sets else np.zeros(0, dtype=np.int64)
+        return None if len(tiles) > 0.75 * total_tiles else tiles
 
     # -- persistence (the Qdrant volume of docker-compose.yml:26-27) ----------------------------------
     def save(self, path: str, chunk_rows: int = 1 << 20) -> None:
@@ -217,6 +258,8 @@ class Collection:
                 if not int(codes[row]) & CODE_TOMBSTONE:
                     c._row_of_id[pid] = row
         c._codes = codes.astype(np.uint32)
+        for s in range(0, n, 1 << 20):
+            c._note_tiles(s, c._codes[s:s + (1 << 20)])
         c._tickers = {k: int(v) for k, v in meta["tickers"].items()}
         c._doctypes = {k: int(v) for k, v in meta["doctypes"].items()}
         return c

@@ -449,7 +449,8 @@ static int scan_grid(const frs_index* ix, uint32_t num_tiles) {
 
 // prep -> scan -> merge on `st`.  Exactly one of (out_s32) / (out_s64) may be null.
 static int search_impl(frs_index* ix, const float* q, const uint32_t* code, const uint32_t* mask, int nq,
-                       int k, float* out_s32, double* out_s64, int64_t* out_ids, cudaStream_t st) {
+                       int k, float* out_s32, double* out_s64, int64_t* out_ids, cudaStream_t st,
+                       const uint32_t* tile_ids = nullptr, int64_t n_tile_ids = 0) {
   if (!ix) return set_err(FRS_E_INVALID, "idx is null");
   if (nq < 1 || nq > kNQ) return set_err(FRS_E_INVALID, "nq must be in [1,%d] (got %d)", kNQ, nq);
   if (k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "k must be in [1,%d] (got %d)", kMaxK, k);
@@ -469,7 +470,16 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
   launches++;
   if (pev) CU_TRY(cudaEventRecord(pev[1], st));
   const uint32_t n = (uint32_t)ix->size;
-  const uint32_t num_tiles = (n + kTileM - 1) / kTileM;
+  uint32_t num_tiles = (n + kTileM - 1) / kTileM;
+  // restricted scan: only the listed tiles (the caller guarantees that every row matching any query's
+  // predicate lies in one of them).  A list too long for the per-CTA table falls back to the full scan.
+  if (tile_ids) {
+    const int g = scan_grid(ix, (uint32_t)n_tile_ids);
+    if (n_tile_ids >= 0 && n_tile_ids <= (int64_t)num_tiles && (g == 0 || (n_tile_ids + g - 1) / g <= kMaxTileSlots))
+      num_tiles = (uint32_t)n_tile_ids;
+    else
+      tile_ids = nullptr;
+  }
   const int grid = scan_grid(ix, num_tiles);
   if (grid > 0) {
     ScanParams sp{};
@@ -477,6 +487,7 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
     sp.codes = ix->codes;
     sp.n = n;
     sp.num_tiles = num_tiles;
+    sp.tile_ids = tile_ids;
     sp.qrec = ix->qrec;
     sp.qcode = ix->qcode;
     sp.qmask = ix->qmask;
@@ -528,6 +539,16 @@ extern "C" int frs_index_search(frs_index* idx, const float* dev_queries, const 
   if (!dev_out_scores) return set_err(FRS_E_INVALID, "null pointer argument");
   return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, dev_out_scores, nullptr, dev_out_ids,
                      (cudaStream_t)stream);
+}
+
+extern "C" int frs_index_search_tiles(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
+                                      const uint32_t* dev_q_mask, int nq, int k, const uint32_t* dev_tile_ids,
+                                      int64_t n_tiles, float* dev_out_scores, int64_t* dev_out_ids, void* stream) {
+  if (!dev_out_scores || n_tiles < 0 || (n_tiles > 0 && !dev_tile_ids)) return set_err(FRS_E_INVALID, "bad argument");
+  static uint32_t* dummy = nullptr;  // an empty list is still a restricted scan (nothing can match)
+  if (n_tiles == 0 && !dummy) CU_TRY(cudaMalloc(&dummy, 4));
+  return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, dev_out_scores, nullptr, dev_out_ids,
+                     (cudaStream_t)stream, n_tiles ? dev_tile_ids : dummy, n_tiles);
 }
 
 extern "C" int frs_index_search_local(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,

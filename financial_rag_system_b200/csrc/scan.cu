@@ -58,7 +58,8 @@ struct ScanSmem {
   static constexpr size_t bars = stage + (size_t)kEpiWarps * 32 * (kQW + 1) * 4;  // full[R] empty[R] tfull[A] tempty[A] qbar
   static constexpr size_t nbars = 2 * C::kRing + 2 * kAccStages + 1;
   static constexpr size_t holder = bars + nbars * 8;  // u32 TMEM base, u32 epilogue-done flag
-  static constexpr size_t total = holder + 16;
+  static constexpr size_t tiles = holder + 16;        // u32 [kMaxTileSlots]: this CTA's tiles of a restricted scan
+  static constexpr size_t total = tiles + (size_t)kMaxTileSlots * 4;
 };
 
 size_t scan_smem_bytes(bool f32) {
@@ -426,6 +427,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
   uint64_t* tempty = tfull + kAccStages;
   uint64_t* qbar = tempty + kAccStages;
   uint32_t* holder = reinterpret_cast<uint32_t*>(sm + S::holder);
+  uint32_t* stile = reinterpret_cast<uint32_t*>(sm + S::tiles);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -451,6 +453,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
     lmax[t] = f32_ordered(-INFINITY);
   }
   if (threadIdx.x == 0) holder[1] = 0u;  // epilogue-done flag for the refresher warp
+  // Restricted scan (ticker-segmented search): slot t of the tile sequence is tile p.tile_ids[t]; this
+  // CTA's slots blockIdx.x, +G, +2G ... are staged in shared memory once.  Full scan: slot == tile.
+  if (p.tile_ids)
+    for (uint32_t i = threadIdx.x; blockIdx.x + i * gridDim.x < p.num_tiles; i += blockDim.x)
+      stile[i] = __ldg(p.tile_ids + blockIdx.x + i * gridDim.x);
+#define FRS_TILE(lt) (p.tile_ids ? stile[(lt)] : blockIdx.x + (lt) * gridDim.x)
   if (warp == 1) {
     tmem_alloc(holder, kTmemCols);
     tmem_relinquish();
@@ -473,7 +481,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
       for (int s = 0; s < C::kSlabs; ++s)
         tma_load_2d(qop + s * C::kQSlabBytes, &tmap_q, qbar, s * C::kSlabK, 0, kEvictLast);
       uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (uint32_t slot = blockIdx.x, plt = 0; slot < p.num_tiles; slot += gridDim.x, ++plt) {
+        const uint32_t tile = FRS_TILE(plt);
         for (int s = 0; s < C::kSlabs; ++s, ++it) {
           const uint32_t stage = it % C::kRing;
           const uint32_t ph = (it / C::kRing) & 1;
@@ -533,9 +542,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
     // Payload codes are prefetched three tiles ahead.  Under the scan's own traffic (~24 MB of TMA
     // requests in flight chip-wide) a DRAM access takes a few microseconds, more than one tile
     // period, and must not sit on the per-tile critical path of the epilogue.
-    auto load_code = [&](uint32_t t) -> uint32_t {
-      const uint32_t r = t * kTileM + lg * 32 + lane;
-      return (t < p.num_tiles && r < p.n) ? __ldg(p.codes + r) : 0xFFFFFFFFu;
+    auto load_code = [&](uint32_t l) -> uint32_t {  // l = local tile counter of this CTA
+      if (blockIdx.x + l * gridDim.x >= p.num_tiles) return 0xFFFFFFFFu;
+      const uint32_t r = FRS_TILE(l) * kTileM + lg * 32 + lane;
+      return r < p.n ? __ldg(p.codes + r) : 0xFFFFFFFFu;
     };
     if constexpr (!DUMP) {
       // Bootstrap thresholds from the prep kernel's sample (lane = query): the k-th largest X of
@@ -558,11 +568,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
       }
       named_bar_sync(1, kEpiThreads);
     }
-    uint32_t code_a = load_code(blockIdx.x);
-    uint32_t code_b = load_code(blockIdx.x + gridDim.x);
-    uint32_t code_c = load_code(blockIdx.x + 2 * gridDim.x);
+    uint32_t code_a = load_code(0);
+    uint32_t code_b = load_code(1);
+    uint32_t code_c = load_code(2);
 
-    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+    for (uint32_t slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x, ++lt) {
+      const uint32_t tile = FRS_TILE(lt);
       const uint32_t acc = lt % kAccStages;
       const uint32_t aph = (lt / kAccStages) & 1;
       const uint32_t row = tile * kTileM + lg * 32 + lane;
@@ -570,7 +581,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
       const uint32_t code = code_a;
       code_a = code_b;
       code_b = code_c;
-      code_c = load_code(tile + 3 * gridDim.x);
+      code_c = load_code(lt + 3);
       const unsigned long long tw0 = p.timeline ? globaltimer_ns() : 0;
       mbar_wait(&tfull[acc], aph);
       if (p.timeline) t_wait += globaltimer_ns() - tw0;

@@ -22,6 +22,7 @@ constexpr int kScanThreads = 64 + kEpiThreads + 32;  // warp0 TMA, warp1 MMA, ep
 constexpr int kMergeThreads = 256;
 constexpr int kGmaxPerLane = 5;                 // cross-CTA bound table: up to 160 CTAs
 constexpr int kGmaxPad = 32 * kGmaxPerLane;     // floats per query
+constexpr int kMaxTileSlots = 944;              // tiles per CTA of a restricted scan (what shared memory leaves)
 
 // bootstrap sample scored by the prep kernel: kSampleBlocks blocks x kSampleRows rows
 constexpr int kSampleBlocks = 64;
@@ -38,7 +39,8 @@ struct ScanParams {
   const void* rows;        // [capacity, 384] storage dtype
   const uint32_t* codes;   // [capacity] payload codes
   uint32_t n;              // rows in use
-  uint32_t num_tiles;      // ceil(n / 128)
+  uint32_t num_tiles;      // tiles to scan: ceil(n / 128), or the length of tile_ids
+  const uint32_t* tile_ids;  // null = every tile; else ascending 128-row tile numbers (restricted scan)
   const float* qrec;       // [32, 384] prepared queries widened to fp32 (exact rescoring operand)
   const uint32_t* qcode;   // [32]
   const uint32_t* qmask;   // [32]

@@ -159,6 +159,34 @@ class VectorIndex:
         check(self._lib.frs_index_search_host(self._h, _ptr(q), _ptr(qc), _ptr(qm), nq, k, _ptr(scores), _ptr(ids)))
         return ids, scores
 
+    def search_tiles(self, queries, q_code, q_mask, k: int, tile_ids):
+        """Exact search restricted to the listed 128-row tiles (ascending unique int32/uint32 array;
+        numpy or torch).  Queries may be numpy (copied) or device tensors; returns device tensors."""
+        q = torch.as_tensor(queries).to(device=self.device, dtype=torch.float32).contiguous()
+        nq = q.shape[0]
+        self._check_batch(nq, k)
+        qc = self._as_code_tensor(q_code)
+        qm = self._as_code_tensor(q_mask)
+        if isinstance(tile_ids, torch.Tensor):
+            t = tile_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(tile_ids, dtype=np.int64).astype(np.int32)).to(self.device)
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        check(self._lib.frs_index_search_tiles(self._h, _ptr(q), _ptr(qc), _ptr(qm), nq, k, _ptr(t), int(t.numel()),
+                                               _ptr(scores), _ptr(ids), _stream_ptr(self.device)))
+        for x in (q, qc, qm, t):
+            x.record_stream(torch.cuda.current_stream(self.device))
+        return ids, scores
+
+    def _as_code_tensor(self, c) -> torch.Tensor:
+        """uint32 payload words (numpy or torch, any integer dtype) as the int32 bit pattern the ABI reads."""
+        if isinstance(c, torch.Tensor) and c.dtype == torch.int32:
+            return c.to(self.device).contiguous()
+        c = torch.as_tensor(np.asarray(c.cpu() if isinstance(c, torch.Tensor) else c, dtype=np.int64) & 0xFFFFFFFF)
+        c = torch.where(c >= (1 << 31), c - (1 << 32), c)
+        return c.to(torch.int32).to(self.device).contiguous()
+
     def search_local(self, q: torch.Tensor, qc: torch.Tensor, qm: torch.Tensor, k: int,
                      out_scores64: torch.Tensor, out_ids: torch.Tensor) -> None:
         """Shard-local pass of a sharded search: exact local top-k as (float64, int64 global id)."""

@@ -132,6 +132,15 @@ int frs_index_search_host(frs_index* idx, const float* host_queries, const uint3
                           const uint32_t* host_q_mask, int nq, int k, float* host_out_scores,
                           int64_t* host_out_ids);
 
+/* Ticker-segmented search: the same exact search restricted to the listed 128-row tiles
+ * (tile t = rows [128 t, 128 t + 128); ascending, unique).  The caller guarantees that every row that
+ * can match ANY query's predicate lies in a listed tile — ingest is per ticker (ingest.py:109-177), so
+ * a ticker's rows occupy few tiles and a filtered batch reads only those.  Rows inside the tiles are
+ * still filtered by the per-query predicate, so the result is identical to frs_index_search. */
+int frs_index_search_tiles(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
+                           const uint32_t* dev_q_mask, int nq, int k, const uint32_t* dev_tile_ids,
+                           int64_t n_tiles, float* dev_out_scores, int64_t* dev_out_ids, void* stream);
+
 /* Sharded search (one shard per GPU / process): local pass that leaves the
  * shard's exact top-k as (fp64 score, int64 global id) pairs for the exchange
  * step, and the final merge over the gathered [n_shards, nq, k] candidates. */

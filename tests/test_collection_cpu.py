@@ -30,6 +30,21 @@ class OracleIndex:
         return ids, sc.astype(np.float32)
 
     dtype = "f32"
+    tiles_seen = None
+
+    def search_tiles(self, q, code, mask, k, tile_ids):
+        """Restricted scan double: ONLY rows of the listed tiles exist for this search."""
+        import torch
+
+        tiles = np.asarray(tile_ids, dtype=np.int64)
+        OracleIndex.tiles_seen = tiles
+        keep = np.zeros(len(self.rows), dtype=bool)
+        for t in tiles:
+            keep[t * 128:(t + 1) * 128] = True
+        sel = np.flatnonzero(keep)
+        ids, sc = so.exact_topk(self.rows[sel], so.prepare_queries(q, "f32"), self.codes[sel], code, mask, k)
+        ids = np.where(ids >= 0, sel[np.maximum(ids, 0)] if len(sel) else -1, -1)
+        return torch.from_numpy(ids.astype(np.int64)), torch.from_numpy(sc.astype(np.float32))
 
     def set_rows(self, row0, vecs, codes=None):
         v = so.store_rows(vecs.cpu().numpy(), "f32")
@@ -215,3 +230,37 @@ def test_save_and_load_round_trip(tmp_path):
     assert len(d) == len(c)
     got, sc = d.search(vecs[3:4], payloads[0]["ticker"], limit=2)
     assert got[0, 0] == 0 and abs(sc[0, 0] - 1.0) < 1e-6
+
+
+def test_ticker_segmented_search_reads_only_the_tickers_tiles_and_changes_nothing():
+    """rows ingested ticker by ticker (ingest.py:109-177) -> a filtered batch is answered from
+    the tiles of its tickers only, with exactly the ids / scores of the full scan."""
+    rng = np.random.default_rng(4)
+    n_t, per = 12, 700
+    vecs = rng.standard_normal((n_t * per, 384)).astype(np.float32)
+    payloads = [{"ticker": f"T{t}", "document_type": ("10-K", "10-Q")[i % 2], "text": ""} for t in range(n_t) for i in range(per)]
+    ids = list(range(n_t * per))
+    seg = Collection(n_t * per + 10, index=OracleIndex(0))
+    assert seg.segmented
+    for s in range(0, len(ids), 256):
+        seg.upsert(ids[s:s + 256], vecs[s:s + 256], payloads[s:s + 256])
+    full = Collection(n_t * per + 10, index=OracleIndex(0))
+    full.segmented = False
+    full.upsert(ids, vecs, payloads)
+    q = vecs[[5, 800, 4000, 8399]] + 0.1
+    ts = ["T0", "T1", "T5", "T11"]
+    a = seg.search(q, ts, 15, ["10-K", None, None, "10-Q"])
+    b = full.search(q, ts, 15, ["10-K", None, None, "10-Q"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    scanned, total = seg.last_scan_tiles
+    assert total == (n_t * per + 127) // 128 and scanned <= 4 * (per // 128 + 2) < total / 2
+    # a query without ticker condition needs every row: full scan
+    seg.search(q[:1], None, 5)
+    assert seg.last_scan_tiles == (total, total)
+    # unknown ticker: nothing to read, nothing returned
+    got, sc = seg.search(q[:1], "NOPE", 5)
+    assert (got == -1).all() and seg.last_scan_tiles[0] == 0
+    # a row re-upserted under another ticker is found under the new one
+    seg.upsert([ids[3]], vecs[3:4], [{"ticker": "T7", "document_type": "10-K", "text": ""}])
+    got, sc = seg.search(vecs[3:4], "T7", 1)
+    assert got[0, 0] == 3

@@ -380,3 +380,61 @@ def test_export_import_raw_round_trip_is_bit_exact():
             b.import_raw(rows.astype(np.float64), c)
         a.close()
         b.close()
+
+
+def test_restricted_scan_equals_full_scan():
+    """frs_index_search_tiles: scanning only the tiles that can hold matches returns the ids and score
+    bits of the full scan (ticker-grouped rows, several grid sizes, empty and single-tile lists)."""
+    from financial_rag_system_b200.index import VectorIndex
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n_t, per, nq, k = 40, 3000, 32, 15
+    n = n_t * per
+    x = torch.randn((n, 384), generator=g, device="cuda")
+    codes = (torch.arange(n, device="cuda") // per + 1).to(torch.int32)          # ticker-grouped ingest order
+    src = torch.randint(0, n, (nq,), generator=g, device="cuda")
+    q = x[src] + 0.05 * torch.randn((nq, 384), generator=g, device="cuda")
+    qc = codes[src].clone()
+    qc[5:] = qc[5 + (torch.arange(nq - 5, device="cuda") % 3)]                   # 8 distinct tickers in the batch
+    qm = torch.full((nq,), 0x80FFFFFF - (1 << 32), dtype=torch.int64).to(torch.int32).cuda()
+    for dtype in ("bf16", "f32"):
+        ix = VectorIndex(n, dtype=dtype, device=0)
+        ix.add(x, codes)
+        ids_f, s_f = ix.search(q, qc, qm, k)
+        tiles = np.unique(np.concatenate([np.arange((int(c) - 1) * per // 128, ((int(c) - 1) * per + per - 1) // 128 + 1)
+                                          for c in qc.cpu().numpy()]))
+        assert len(tiles) < (n + 127) // 128 // 3
+        for grid in (0, 1, 7, 148):
+            ix.set_scan_grid(grid)
+            ids_t, s_t = ix.search_tiles(q, qc, qm, k, tiles)
+            torch.cuda.synchronize()
+            assert torch.equal(ids_t, ids_f) and torch.equal(s_t, s_f), (dtype, grid)
+        ix.set_scan_grid(0)
+        one = np.array([int(src[0]) // 128])
+        ids_1, s_1 = ix.search_tiles(q[:1], qc[:1], qm[:1], k, one)
+        assert int(ids_1[0, 0]) == int(src[0])
+        ids_0, s_0 = ix.search_tiles(q, qc, qm, k, np.zeros(0, dtype=np.int64))
+        torch.cuda.synchronize()
+        assert (ids_0 == -1).all() and torch.isinf(s_0).all()
+        ix.close()
+
+
+def test_collection_on_gpu_uses_the_restricted_scan():
+    from financial_rag_system_b200.collection import Collection
+
+    rng = np.random.default_rng(6)
+    n_t, per = 10, 2000
+    vecs = rng.standard_normal((n_t * per, 384)).astype(np.float32)
+    payloads = [{"ticker": f"T{t}", "document_type": "10-K", "text": ""} for t in range(n_t) for _ in range(per)]
+    seg = Collection(n_t * per, dtype="bf16", device=0)
+    seg.upsert(list(range(n_t * per)), vecs, payloads)
+    q = vecs[[10, 2500, 19990]] + 0.05
+    ts = ["T0", "T1", "T9"]
+    a = seg.search(q, ts, 15)
+    scanned, total = seg.last_scan_tiles
+    assert scanned < total / 2
+    seg.segmented = False
+    b = seg.search(q, ts, 15)
+    assert seg.last_scan_tiles == (total, total)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    seg.close()
