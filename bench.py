@@ -258,6 +258,14 @@ def run_ours(args):
         gq = torch.Generator(device=dev).manual_seed(11)
         q = first_rows + 0.02 * torch.randn((NQ, DIM), generator=gq, device=dev)
         qc = first_codes
+    q_rows = None
+    if grouped:
+        # queries about rows spread over the corpus (row-proportional, i.e. tickers ~ the corpus' Zipf)
+        q_rows = np.sort(np.random.default_rng(11).integers(0, length, NQ))
+        src = torch.cat([ix.read_rows(int(r), 1) for r in q_rows])
+        gq = torch.Generator(device=dev).manual_seed(11)
+        q = src + 0.02 * torch.randn((NQ, DIM), generator=gq, device=dev)
+        qc = torch.searchsorted(cum, torch.tensor(q_rows, dtype=torch.float64, device=dev), right=True).clamp_(max=N_TICKERS - 1).to(torch.int32)
     if world > 1:
         dist.broadcast(q, 0)
         dist.broadcast(qc, 0)
@@ -313,7 +321,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ids, scores = last.wait() if sh is not None else last
-    assert int(ids[0, 0].item()) == 0, "query 0 is a perturbed copy of global row 0"
+    if grouped:
+        assert ids[:, 0].cpu().numpy().tolist() == q_rows.tolist(), "every query is a perturbed copy of its source row"
+    else:
+        assert int(ids[0, 0].item()) == 0, "query 0 is a perturbed copy of global row 0"
 
     # ---- timed region B: per-kernel events (roofline of the scan kernel) ----
     ix.set_profiling(1)
