@@ -97,6 +97,25 @@ cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* row_start, int
 // out[t] = fp32(x[row_of_tok[t]]) for the caller's packed tokens
 cudaError_t launch_gather_rows_f32(const __nv_bfloat16* x, const int32_t* row_of_tok, int n_tokens, float* out,
                                    cudaStream_t st);
+// ---- fp32 mode (bert_fp32.cu): fp32 weights / activations / FFMA arithmetic, for the 1e-5 parity bound ----
+// epi: 0 = +bias, 1 = +bias then erf GELU, 2 = +bias +residual.  C = A[M,K] . W[N,K]^T; N % 128 == 0, K % 16 == 0
+cudaError_t launch_sgemm(int epi, const float* A, const float* W, const float* bias, const float* resid, float* C,
+                         int M, int N, int K, cudaStream_t st);
+cudaError_t launch_embed_ln_f32(const int32_t* ids, const int32_t* type_ids, const int32_t* src_tok,
+                                const int32_t* pos_of_row, int M, int vocab, const float* word, const float* pos,
+                                const float* type, const float* gamma, const float* beta, float eps, float* x,
+                                cudaStream_t st);
+cudaError_t launch_layernorm_f32(const float* x, int M, const float* gamma, const float* beta, float eps, float* y,
+                                 cudaStream_t st);
+// qkv: [rows, 1152] = q | k | v (unscaled); one block per (query block, head)
+cudaError_t launch_attention_f32(const float* qkv, const QBlock* qblk, int nqb, float* ctx, cudaStream_t st);
+cudaError_t launch_pool_normalize_f32(const float* x, const int32_t* cu_seqlens, const int32_t* row_start, int n_seqs,
+                                      int pool_mode, float* out, cudaStream_t st);
+cudaError_t launch_ce_head_f32(const float* x, const int32_t* row_start, int n_seqs, const float* wp, const float* bp,
+                               const float* wc, const float* bc, float* logits, cudaStream_t st);
+cudaError_t launch_gather_rows_f32f32(const float* x, const int32_t* row_of_tok, int n_tokens, float* out,
+                                      cudaStream_t st);
+
 // mapped host words {wait code, blockIdx, parity, threadIdx} written by a barrier wait that timed out
 uint32_t* bert_trap_info_host();
 cudaError_t launch_bf16_to_f32(const __nv_bfloat16* src, int64_t n, float* dst, cudaStream_t st);

@@ -35,6 +35,7 @@ enum ProfClass { kPEmbed = 0, kPQkv, kPAttn, kPOut, kPUp, kPDown, kPHead, kPClas
 
 struct Layer {
   __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *wqkv32 = nullptr, *wo32 = nullptr, *w132 = nullptr, *w232 = nullptr;  // fp32 mode
   float *bqkv = nullptr, *bo = nullptr, *ln1g = nullptr, *ln1b = nullptr, *b1 = nullptr, *b2 = nullptr,
         *ln2g = nullptr, *ln2b = nullptr;
   CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
@@ -55,6 +56,8 @@ struct frs_encoder {
   std::vector<void*> owned;  // every device allocation, freed in destroy
   // activations (packed tokens)
   __nv_bfloat16 *x0 = nullptr, *x1 = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *h = nullptr;
+  float *fx0 = nullptr, *fx1 = nullptr, *fqkv = nullptr, *fctx = nullptr, *fh = nullptr, *ftmp = nullptr;  // fp32 mode
+  bool f32() const { return cfg.precision == FRS_PRECISION_F32; }
   int32_t *pos_of_row = nullptr, *src_tok = nullptr, *row_of_tok = nullptr;
   int32_t *d_cu = nullptr, *d_rs = nullptr;  // caller cu_seqlens | internal row starts (multiples of 8)
   QBlock* d_qblk = nullptr;
@@ -136,6 +139,8 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
     return abi_set_err(FRS_E_INVALID,
                        "unsupported BERT shape: need hidden 384, heads 12, intermediate 1536, max_pos 512, "
                        "type_vocab 2, 1..%d layers", FRS_MAX_LAYERS);
+  if (cfg->precision != FRS_PRECISION_BF16 && cfg->precision != FRS_PRECISION_F32)
+    return abi_set_err(FRS_E_INVALID, "precision must be FRS_PRECISION_BF16 or FRS_PRECISION_F32");
   if (n_weights != FRS_BERT_WEIGHTS(cfg->layers, cfg->has_head))
     return abi_set_err(FRS_E_INVALID, "expected %d weight tensors, got %d", FRS_BERT_WEIGHTS(cfg->layers, cfg->has_head),
                        n_weights);
@@ -186,12 +191,27 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   for (int l = 0; l < cfg->layers; ++l) {
     Layer& L = e->layers[l];
     const float* const* lw = w + 5 + 16 * l;
-    EN_TRY(dev_alloc(e, &L.wqkv, (size_t)kQkvN * kHid * 2, false));
+    const cudaMemcpyKind mk = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     EN_TRY(dev_alloc(e, &L.bqkv, (size_t)kQkvN * 4, false));
-    for (int j = 0; j < 3; ++j) {
-      EN_TRY(upload_bf16(e, L.wqkv + (size_t)j * kHid * kHid, lw[2 * j], (size_t)kHid * kHid, dev, scratch));
-      EN_TRY(cudaMemcpy(L.bqkv + j * kHid, lw[2 * j + 1], kHid * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    for (int j = 0; j < 3; ++j) EN_TRY(cudaMemcpy(L.bqkv + j * kHid, lw[2 * j + 1], kHid * 4, mk));
+    if (cfg->precision == FRS_PRECISION_F32) {
+      EN_TRY(dev_alloc(e, &L.wqkv32, (size_t)kQkvN * kHid * 4, false));
+      for (int j = 0; j < 3; ++j) EN_TRY(cudaMemcpy(L.wqkv32 + (size_t)j * kHid * kHid, lw[2 * j], (size_t)kHid * kHid * 4, mk));
+      EN_TRY(upload_f32(e, &L.wo32, lw[6], (size_t)kHid * kHid, dev));
+      EN_TRY(upload_f32(e, &L.w132, lw[10], (size_t)kFfn * kHid, dev));
+      EN_TRY(upload_f32(e, &L.w232, lw[12], (size_t)kHid * kFfn, dev));
+      EN_TRY(upload_f32(e, &L.bo, lw[7], kHid, dev));
+      EN_TRY(upload_f32(e, &L.ln1g, lw[8], kHid, dev));
+      EN_TRY(upload_f32(e, &L.ln1b, lw[9], kHid, dev));
+      EN_TRY(upload_f32(e, &L.b1, lw[11], kFfn, dev));
+      EN_TRY(upload_f32(e, &L.b2, lw[13], kHid, dev));
+      EN_TRY(upload_f32(e, &L.ln2g, lw[14], kHid, dev));
+      EN_TRY(upload_f32(e, &L.ln2b, lw[15], kHid, dev));
+      continue;
     }
+    EN_TRY(dev_alloc(e, &L.wqkv, (size_t)kQkvN * kHid * 2, false));
+    for (int j = 0; j < 3; ++j)
+      EN_TRY(upload_bf16(e, L.wqkv + (size_t)j * kHid * kHid, lw[2 * j], (size_t)kHid * kHid, dev, scratch));
     EN_TRY(dev_alloc(e, &L.wo, (size_t)kHid * kHid * 2, false));
     EN_TRY(upload_bf16(e, L.wo, lw[6], (size_t)kHid * kHid, dev, scratch));
     EN_TRY(upload_f32(e, &L.bo, lw[7], kHid, dev));
@@ -218,12 +238,21 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
     EN_TRY(upload_f32(e, &e->cls_b, hw[3], 1, dev));
   }
   // activations: zero-initialised so that rows beyond the live tokens are always finite
-  EN_TRY(dev_alloc(e, &e->x0, T * kHid * 2, true));
-  EN_TRY(dev_alloc(e, &e->x1, T * kHid * 2, true));
-  EN_TRY(dev_alloc(e, &e->qk, T * 2 * kHid * 2, true));
-  EN_TRY(dev_alloc(e, &e->vt, T * kHid * 2, true));
-  EN_TRY(dev_alloc(e, &e->ctx, T * kHid * 2, true));
-  EN_TRY(dev_alloc(e, &e->h, T * kFfn * 2, true));
+  if (cfg->precision == FRS_PRECISION_F32) {
+    EN_TRY(dev_alloc(e, &e->fx0, T * kHid * 4, true));
+    EN_TRY(dev_alloc(e, &e->fx1, T * kHid * 4, true));
+    EN_TRY(dev_alloc(e, &e->fqkv, T * kQkvN * 4, true));
+    EN_TRY(dev_alloc(e, &e->fctx, T * kHid * 4, true));
+    EN_TRY(dev_alloc(e, &e->fh, T * kFfn * 4, true));
+    EN_TRY(dev_alloc(e, &e->ftmp, T * kHid * 4, true));
+  } else {
+    EN_TRY(dev_alloc(e, &e->x0, T * kHid * 2, true));
+    EN_TRY(dev_alloc(e, &e->x1, T * kHid * 2, true));
+    EN_TRY(dev_alloc(e, &e->qk, T * 2 * kHid * 2, true));
+    EN_TRY(dev_alloc(e, &e->vt, T * kHid * 2, true));
+    EN_TRY(dev_alloc(e, &e->ctx, T * kHid * 2, true));
+    EN_TRY(dev_alloc(e, &e->h, T * kFfn * 2, true));
+  }
   EN_TRY(dev_alloc(e, &e->pos_of_row, T * 4, true));
   EN_TRY(dev_alloc(e, &e->src_tok, T * 4, true));
   EN_TRY(dev_alloc(e, &e->row_of_tok, T * 4, true));
@@ -242,6 +271,10 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   EN_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   EN_TRY(cudaEventCreateWithFlags(&e->staged, cudaEventDisableTiming));
   EN_TRY(cudaEventCreateWithFlags(&e->ws_free, cudaEventDisableTiming));
+  if (cfg->precision == FRS_PRECISION_F32) {
+    *out = e;
+    return FRS_OK;
+  }
   EN_RC(abi_make_tmap_bf16(&e->t_x0, e->x0, T, kHid, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_x1, e->x1, T, kHid, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_ctx, e->ctx, T, kHid, 64, kBM));
@@ -327,6 +360,29 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
   if (e->prof) CU_TRY(cudaEventRecord(e->pev[0], st));
   int rc;
   CU_TRY(launch_row_map(e->d_cu, e->d_rs, n_seqs, e->src_tok, e->pos_of_row, e->row_of_tok, st));
+  if (e->f32()) {
+    // fp32 mode: the same graph with fp32 FFMA kernels (bert_fp32.cu); LayerNorm is a separate kernel here
+    CU_TRY(launch_embed_ln_f32(d_ids, d_type, e->src_tok, e->pos_of_row, M, e->cfg.vocab_size, e->word, e->pos, e->type,
+                               e->emb_g, e->emb_b, e->cfg.ln_eps, e->fx0, st));
+    if ((rc = prof_mark(e, kPEmbed, st))) return rc;
+    for (int l = 0; l < e->cfg.layers; ++l) {
+      const Layer& L = e->layers[l];
+      CU_TRY(launch_sgemm(0, e->fx0, L.wqkv32, L.bqkv, nullptr, e->fqkv, M, kQkvN, kHid, st));
+      if ((rc = prof_mark(e, kPQkv, st))) return rc;
+      CU_TRY(launch_attention_f32(e->fqkv, e->d_qblk, nqb, e->fctx, st));
+      if ((rc = prof_mark(e, kPAttn, st))) return rc;
+      CU_TRY(launch_sgemm(2, e->fctx, L.wo32, L.bo, e->fx0, e->ftmp, M, kHid, kHid, st));
+      CU_TRY(launch_layernorm_f32(e->ftmp, M, L.ln1g, L.ln1b, e->cfg.ln_eps, e->fx1, st));
+      if ((rc = prof_mark(e, kPOut, st))) return rc;
+      CU_TRY(launch_sgemm(1, e->fx1, L.w132, L.b1, nullptr, e->fh, M, kFfn, kHid, st));
+      if ((rc = prof_mark(e, kPUp, st))) return rc;
+      CU_TRY(launch_sgemm(2, e->fh, L.w232, L.b2, e->fx1, e->ftmp, M, kHid, kFfn, st));
+      CU_TRY(launch_layernorm_f32(e->ftmp, M, L.ln2g, L.ln2b, e->cfg.ln_eps, e->fx0, st));
+      if ((rc = prof_mark(e, kPDown, st))) return rc;
+    }
+    e->last_tokens = host_cu[n_seqs];
+    return FRS_OK;
+  }
   CU_TRY(launch_embed_ln(d_ids, d_type, e->src_tok, e->pos_of_row, M, e->cfg.vocab_size, e->word, e->pos, e->type, e->emb_g,
                          e->emb_b, e->cfg.ln_eps, e->x0, st));
   if ((rc = prof_mark(e, kPEmbed, st))) return rc;
@@ -387,7 +443,10 @@ extern "C" int frs_encoder_embed(frs_encoder* enc, const int32_t* dev_ids, const
   cudaStream_t st = (cudaStream_t)stream;
   int rc = forward(enc, dev_ids, nullptr, host_cu_seqlens, n_seqs, st);
   if (rc) return rc;
-  CU_TRY(launch_pool_normalize(enc->x0, enc->d_cu, enc->d_rs, n_seqs, pool_mode, dev_out, st));
+  if (enc->f32())
+    CU_TRY(launch_pool_normalize_f32(enc->fx0, enc->d_cu, enc->d_rs, n_seqs, pool_mode, dev_out, st));
+  else
+    CU_TRY(launch_pool_normalize(enc->x0, enc->d_cu, enc->d_rs, n_seqs, pool_mode, dev_out, st));
   if ((rc = prof_mark(enc, kPHead, st))) return rc;
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;
@@ -403,7 +462,10 @@ extern "C" int frs_encoder_score_pairs(frs_encoder* enc, const int32_t* dev_ids,
   cudaStream_t st = (cudaStream_t)stream;
   int rc = forward(enc, dev_ids, dev_type_ids, host_cu_seqlens, n_seqs, st);
   if (rc) return rc;
-  CU_TRY(launch_ce_head(enc->x0, enc->d_rs, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
+  if (enc->f32())
+    CU_TRY(launch_ce_head_f32(enc->fx0, enc->d_rs, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
+  else
+    CU_TRY(launch_ce_head(enc->x0, enc->d_rs, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
   if ((rc = prof_mark(enc, kPHead, st))) return rc;
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;
@@ -472,7 +534,10 @@ extern "C" int frs_encoder_last_hidden(frs_encoder* enc, float* dev_out, int n_t
   cudaStream_t st = (cudaStream_t)stream;
   CU_TRY(cudaStreamWaitEvent(st, enc->ws_free, 0));
   if (n_tokens > enc->last_tokens) return abi_set_err(FRS_E_INVALID, "the last pass had %d tokens", enc->last_tokens);
-  CU_TRY(launch_gather_rows_f32(enc->x0, enc->row_of_tok, n_tokens, dev_out, st));
+  if (enc->f32())
+    CU_TRY(launch_gather_rows_f32f32(enc->fx0, enc->row_of_tok, n_tokens, dev_out, st));
+  else
+    CU_TRY(launch_gather_rows_f32(enc->x0, enc->row_of_tok, n_tokens, dev_out, st));
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;
 }
@@ -483,6 +548,7 @@ extern "C" int frs_encoder_debug_read(frs_encoder* enc, int which, float* dev_ou
   const __nv_bfloat16* src[6] = {enc->x0, enc->x1, enc->qk, enc->vt, enc->ctx, enc->h};
   const int64_t cap[6] = {T * kHid, T * kHid, T * 2 * kHid, T * kHid, T * kHid, T * kFfn};
   if (which < 0 || which > 5 || n_elems > cap[which]) return abi_set_err(FRS_E_INVALID, "bad buffer / size");
+  if (enc->f32()) return abi_set_err(FRS_E_STATE, "debug_read reads the bf16 workspace; this encoder runs in fp32 mode");
   CU_TRY(cudaSetDevice(enc->device));
   std::lock_guard<std::mutex> lk(enc->mu);
   cudaStream_t st = (cudaStream_t)stream;

@@ -27,7 +27,10 @@ POOL_CLS, POOL_MEAN = 0, 1
 class _BertCfg(C.Structure):
     _fields_ = [("vocab_size", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
                 ("intermediate", C.c_int32), ("max_pos", C.c_int32), ("type_vocab", C.c_int32),
-                ("has_head", C.c_int32), ("ln_eps", C.c_float)]
+                ("has_head", C.c_int32), ("ln_eps", C.c_float), ("precision", C.c_int32)]
+
+
+PRECISIONS = {"bf16": 0, "fp32": 1, "f32": 1}
 
 
 def _np_ptr(a: np.ndarray) -> C.c_void_p:
@@ -37,13 +40,17 @@ def _np_ptr(a: np.ndarray) -> C.c_void_p:
 class BertEncoder:
     """Handle on one `frs_encoder` (weights + workspace on one GPU)."""
 
-    def __init__(self, shape: BertShape, weights: dict, device: int = 0, max_tokens: int = 65536):
+    def __init__(self, shape: BertShape, weights: dict, device: int = 0, max_tokens: int = 65536,
+                 precision: str = "bf16"):
+        """precision "bf16": tensor-core path (bf16 operands/activations, fp32 accumulation);
+        "fp32": fp32 FFMA kernels end to end (~20x slower; error < 1e-5, the parity mode)."""
         self._lib = _lib.lib()
         self.shape = shape
         self.device = int(device)
+        self.precision = "fp32" if PRECISIONS[precision] else "bf16"
         table = weight_table(shape, weights)
         cfg = _BertCfg(shape.vocab_size, shape.hidden, shape.layers, shape.heads, shape.intermediate, shape.max_pos,
-                       shape.type_vocab, int(shape.has_head), shape.ln_eps)
+                       shape.type_vocab, int(shape.has_head), shape.ln_eps, PRECISIONS[precision])
         ptrs = (C.c_void_p * len(table))(*[a.ctypes.data for a in table])
         h = C.c_void_p()
         check(self._lib.frs_encoder_create(self.device, C.byref(cfg), ptrs, len(table), 0, int(max_tokens), C.byref(h)))
@@ -160,13 +167,13 @@ class Embedder:
     PIPELINE_TEXTS = 512  # texts per tokenise/encode slice of a large encode() call
 
     def __init__(self, model: str | None = None, device: int = 0, pool: str = "cls", max_tokens: int = 65536,
-                 tokenizer: WordPiece | None = None):
+                 tokenizer: WordPiece | None = None, precision: str = "bf16"):
         shape, weights, tok = _load(model, BGE_SMALL, self.SYNTHETIC_SEED)
         if shape.has_head:
             raise ValueError("an embedding model must not carry a classifier head")
         self.tokenizer = tokenizer or tok
         self.pool = {"cls": POOL_CLS, "mean": POOL_MEAN}[pool]
-        self.bert = BertEncoder(shape, weights, device=device, max_tokens=max_tokens)
+        self.bert = BertEncoder(shape, weights, device=device, max_tokens=max_tokens, precision=precision)
 
     def encode(self, texts, **_ignored) -> np.ndarray:
         single = isinstance(texts, str)
@@ -204,12 +211,12 @@ class Reranker:
     SYNTHETIC_SEED = 4321
 
     def __init__(self, model: str | None = None, device: int = 0, max_tokens: int = 65536,
-                 tokenizer: WordPiece | None = None):
+                 tokenizer: WordPiece | None = None, precision: str = "bf16"):
         shape, weights, tok = _load(model, MINILM_L6_CE, self.SYNTHETIC_SEED)
         if not shape.has_head:
             raise ValueError("a cross-encoder needs the pooler + classifier head")
         self.tokenizer = tokenizer or tok
-        self.bert = BertEncoder(shape, weights, device=device, max_tokens=max_tokens)
+        self.bert = BertEncoder(shape, weights, device=device, max_tokens=max_tokens, precision=precision)
 
     def predict(self, pairs, **_ignored) -> np.ndarray:
         pairs = list(pairs)

@@ -191,7 +191,11 @@ typedef struct frs_bert_cfg {
   int32_t type_vocab;    /* 2     */
   int32_t has_head;      /* 1 = pooler + 1-logit classifier (cross-encoder) */
   float ln_eps;          /* 1e-12 */
+  int32_t precision;     /* FRS_PRECISION_BF16 (tensor cores) or FRS_PRECISION_F32 (fp32 FFMA, parity mode) */
 } frs_bert_cfg;
+
+#define FRS_PRECISION_BF16 0 /* bf16 operands + activations, fp32 accumulation: |embedding error| ~1e-3  */
+#define FRS_PRECISION_F32 1  /* fp32 everywhere, no tensor cores, ~20x slower: |error| < 1e-5          */
 
 #define FRS_MAX_LAYERS 12
 #define FRS_MAX_SEQ 512 /* max_position_embeddings; SentenceTransformer / CrossEncoder truncate here */

@@ -13,6 +13,8 @@ Tolerances (north_star: "1e-2 absolute for bf16"):
                                                           for bf16 is met by embeddings and cosine scores,
                                                           not by this head; measured values are printed.
     per-stage activations of one layer                    <= 0.05 absolute on O(1) values
+fp32 mode (precision="fp32": fp32 weights, activations and FFMA arithmetic, no tensor cores), north_star "1e-5":
+    embedding components <= 1e-5, last hidden state <= 1e-4 on O(5) values, reranker logits <= 1e-4
 """
 import numpy as np
 import pytest
@@ -272,3 +274,43 @@ def test_text_surface_embedder_and_reranker_follow_the_reference_contract():
     assert np.abs(s - ref).max() <= 0.12
     assert rr.predict([]).shape == (0,)
     rr.close()
+
+
+def test_fp32_mode_meets_the_1e5_bound():
+    """north_star: "1e-5 for the fp32 mode".  Same ABI, precision = FRS_PRECISION_F32."""
+    from financial_rag_system_b200.encoder import BertEncoder
+    from oracle import encoder_oracle as eo
+
+    lens = [16, 230, 512, 1, 129, 77]
+    ids, tts, cu = _random_batch(lens, 31, pairs=True)
+    w = synthetic_checkpoint(BGE_SMALL, 1234)
+    enc = BertEncoder(BGE_SMALL, w, device=0, max_tokens=2048, precision="fp32")
+    for pool, name in ((0, "cls"), (1, "mean")):
+        got = enc.embed_packed(ids, cu, pool)
+        ref = eo.embed(BGE_SMALL, w, ids, cu, name)
+        print(f"fp32 {name}: max err {np.abs(got - ref).max():.2e}")
+        assert np.abs(got - ref).max() <= 1e-5
+    hid = enc.last_hidden(int(cu[-1])).cpu().numpy()
+    ref_h = eo.last_hidden_packed(BGE_SMALL, w, ids, cu)
+    print(f"fp32 last hidden: max err {np.abs(hid - ref_h).max():.2e}")
+    assert np.abs(hid - ref_h).max() <= 1e-4
+    enc.close()
+    wc = synthetic_checkpoint(MINILM_L6_CE, 4321)
+    ce32 = BertEncoder(MINILM_L6_CE, wc, device=0, max_tokens=2048, precision="fp32")
+    got = ce32.score_packed(ids, tts, cu)
+    ref = eo.score_pairs(MINILM_L6_CE, wc, ids, tts, cu)
+    print(f"fp32 logits: max err {np.abs(got - ref).max():.2e}")
+    assert np.abs(got - ref).max() <= 1e-4
+    ce32.close()
+
+
+def test_bf16_path_deviates_from_the_fp32_path_by_rounding_only(bge):
+    """The two GPU paths share the structure; their difference is the bf16 rounding noise."""
+    from financial_rag_system_b200.encoder import BertEncoder
+
+    enc, w = bge
+    ids, _, cu = _random_batch([64, 300, 9], 8)
+    e32 = BertEncoder(BGE_SMALL, w, device=0, max_tokens=1024, precision="fp32")
+    a, b = enc.embed_packed(ids, cu), e32.embed_packed(ids, cu)
+    e32.close()
+    assert np.abs(a - b).max() <= 1e-2 and ((a * b).sum(1)).min() >= 0.999
