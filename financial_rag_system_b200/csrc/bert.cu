@@ -223,10 +223,13 @@ struct GemmCfg {
   static constexpr int kTotal = kHolder + 16;
 };
 
-// Output path of every epilogue: registers -> swizzled staging tile in shared memory -> TMA store.
-// (Direct per-thread row stores cost one 16-byte LSU transaction per lane; the staged tile leaves as
-// full 128-byte lines.)  Named barriers 2 / 3 = "staging is free" / "staging is written".
-constexpr uint32_t kBarStageFree = 2, kBarStageFull = 3;
+// Output path of every epilogue: registers -> swizzled staging box in shared memory -> TMA store.
+// (Direct per-thread row stores cost one 16-byte LSU transaction per lane; a staged box leaves as full
+// lines.)  The four warps that own one half of the tile's columns form a group with its own ring of three
+// 8 KB boxes (one 32-column chunk of all 128 rows each) and its own store-issuing thread: a chunk is
+// stored the moment it is staged, and its box is only reused three chunks later — the stores never sit
+// on the epilogue's critical path.  Named barrier 2 + group.
+constexpr int kChunkBox = kBM * 64;  // 128 rows x 32 bf16
 
 // ResLN (bias + residual + LayerNorm over the 384-wide row) runs on a CLUSTER OF TWO CTAs: each CTA owns
 // one 192-column half of the same 128-row tile — the same 2-accumulator pipeline as the other GEMMs, so
@@ -351,11 +354,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t quarter = warp & 3;           // TMEM lanes 32*quarter .. +32 are visible to this warp
     const uint32_t half = (warp - 2) >> 2;       // which half of the tile's columns
     const uint32_t row = quarter * 32 + lane;    // row within the tile
-    const bool issuer = threadIdx.x == 64;       // the epilogue thread that owns the TMA store groups
+    const bool issuer = (threadIdx.x & 127) == 64;  // first thread of each column-half group owns its TMA stores
+    uint8_t* const sgroup = sout0 + half * (3 * kChunkBox);
+    uint32_t nchunk = 0;                         // chunks staged so far by this group (ring position)
     if (issuer) {
       tma_prefetch_desc(&tmap_out);
       if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
     }
+    // stage 32 columns (packed bf16 pairs o[16]) of this thread's row, then store the box [128 rows x 32 cols]
+    auto stage_and_store = [&](const uint32_t (&o)[16], int col, int mt) {
+      uint8_t* box = sgroup + (nchunk % 3) * kChunkBox;
+      uint8_t* dst = box + row * 64;  // SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dst + ((j ^ ((row >> 1) & 3)) << 4)) =
+            make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      fence_proxy_async();
+      named_bar_sync(2 + half, 128);
+      if (issuer) {
+        tma_store_2d(&tmap_out, box, col, mt * kBM);
+        tma_store_commit();
+        tma_store_wait_read<1>();  // the store issued one chunk ago has left shared memory
+      }
+      ++nchunk;
+    };
     uint32_t lt = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
       const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
@@ -383,9 +405,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&tempty[acc]);
       } else if constexpr (EPI == kEpiQKV || EPI == kEpiGelu) {
         const bool transposed = EPI == kEpiQKV && nt * BN >= 2 * kHid;  // value projection
-        uint8_t* sout = sout0;
-        if (issuer) tma_store_wait_read<0>();  // the previous tile's stores have read the staging tile
-        named_bar_sync(kBarStageFree, kGemmEpiThreads);
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
           const int ct = (int)half * C::kColsPerThread + c * 32;  // column within the tile
@@ -397,17 +416,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
           const float* bs = sbias + nt * BN + ct;
-          if (p.debug & 4) continue;
           if (transposed) {
-            // value projection: stored transposed, vt[dim][token], so that it is the K-major B operand
-            // of P.V in the attention kernel.  Staging boxes: [64 dims][64 tokens], SWIZZLE_128B.
+            // value projection: stored transposed, vt[dim][token], so that it is the K-major B operand of
+            // P.V in the attention kernel.  Two boxes [32 dims][64 tokens] (SWIZZLE_128B) per chunk.
+            uint8_t* box = sgroup + (nchunk % 3) * kChunkBox;
+            uint8_t* dst = box + (row >> 6) * 4096 + (row & 7) * 2;
+            const uint32_t tchunk = (row & 63) >> 3;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const uint32_t d = (uint32_t)ct + j;
-              uint8_t* dst = sout + ((d >> 6) * 2 + (row >> 6)) * 8192 + (d & 63) * 128 +
-                             ((((row & 63) >> 3) ^ (d & 7)) << 4) + (row & 7) * 2;
-              *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
+            for (int j = 0; j < 32; ++j)
+              *reinterpret_cast<__nv_bfloat16*>(dst + j * 128 + ((tchunk ^ (j & 7)) << 4)) =
+                  __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
+            fence_proxy_async();
+            named_bar_sync(2 + half, 128);
+            if (issuer) {
+              tma_store_2d(&tmap_out2, box, mt * kBM, nt * BN - 2 * kHid + ct);
+              tma_store_2d(&tmap_out2, box + 4096, mt * kBM + 64, nt * BN - 2 * kHid + ct);
+              tma_store_commit();
+              tma_store_wait_read<1>();
             }
+            ++nchunk;
           } else {
             const float sc = (EPI == kEpiQKV && nt * BN < kHid) ? p.qscale : 1.0f;
             uint32_t o[16];
@@ -424,27 +451,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
               o[j] = pack_bf16x2(a, b);
             }
-            // staging boxes: [128 rows][64 columns], SWIZZLE_128B
-            uint8_t* box = sout + (ct >> 6) * 16384 + row * 128;
-            const uint32_t j0 = (uint32_t)(ct & 63) >> 3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(box + (((j0 + j) ^ (row & 7)) << 4)) =
-                  make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            stage_and_store(o, nt * BN + ct, mt);
           }
-        }
-        fence_proxy_async();
-        named_bar_sync(kBarStageFull, kGemmEpiThreads);
-        if (issuer && !(p.debug & 2)) {
-          if (transposed) {
-#pragma unroll
-            for (int b = 0; b < 6; ++b)
-              tma_store_2d(&tmap_out2, sout + b * 8192, mt * kBM + (b & 1) * 64, nt * BN - 2 * kHid + (b >> 1) * 64);
-          } else {
-#pragma unroll
-            for (int b = 0; b < 3; ++b) tma_store_2d(&tmap_out, sout + b * 16384, nt * BN + b * 64, mt * kBM);
-          }
-          tma_store_commit();
         }
       } else {
         // bias + residual, row statistics of this CTA's 192 columns; the pre-LayerNorm value goes back to
@@ -493,12 +501,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const float mean = tsum * (1.0f / kHid);
         const float var = fmaxf(tsq * (1.0f / kHid) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
-        if (issuer) tma_store_wait_read<0>();  // the previous tile's stores have read the staging tile
-        named_bar_sync(kBarStageFree, kGemmEpiThreads);
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
-          const int ct = (int)half * C::kColsPerThread + c * 32;  // column within this CTA's tile
-          const int col = nt * BN + ct;
+          const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained
@@ -514,19 +519,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
             o[j] = pack_bf16x2(a, b);
           }
-          uint8_t* box = sout0 + (ct >> 6) * 16384 + row * 128;  // [128 rows][64 columns], SWIZZLE_128B
-          const uint32_t j0 = (uint32_t)(ct & 63) >> 3;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(box + (((j0 + j) ^ (row & 7)) << 4)) =
-                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        }
-        fence_proxy_async();
-        named_bar_sync(kBarStageFull, kGemmEpiThreads);
-        if (issuer) {
-#pragma unroll
-          for (int b = 0; b < 3; ++b) tma_store_2d(&tmap_out, sout0 + b * 16384, nt * BN + b * 64, mt * kBM);
-          tma_store_commit();
+          stage_and_store(o, col, mt);
         }
       }
     }

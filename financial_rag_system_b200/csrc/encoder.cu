@@ -61,7 +61,8 @@ struct frs_encoder {
   int32_t *pos_of_row = nullptr, *src_tok = nullptr, *row_of_tok = nullptr;
   int32_t *d_cu = nullptr, *d_rs = nullptr;  // caller cu_seqlens | internal row starts (multiples of 8)
   QBlock* d_qblk = nullptr;
-  CUtensorMap t_x0, t_x1, t_ctx, t_h, t_qk, t_vt;  // box 64 x 128 (vt: 64 x 64): GEMM A operands, attention loads, stores
+  CUtensorMap t_x0, t_x1, t_ctx, t_h, t_qk, t_vt;  // box 64 x 128 (vt: 64 x 64): GEMM A operands, attention loads
+  CUtensorMap s_x0, s_x1, s_h, s_qk, s_vt;         // epilogue stores: box 32 x 128 SWIZZLE_64B (vt: 64 tokens x 32 dims)
   // staging
   int32_t *h_cu = nullptr, *h_rs = nullptr, *h_ids = nullptr, *h_type = nullptr;
   QBlock* h_qblk = nullptr;
@@ -281,6 +282,11 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   EN_RC(abi_make_tmap_bf16(&e->t_h, e->h, T, kFfn, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_qk, e->qk, T, 2 * kHid, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_vt, e->vt, kHid, T, 64, 64));
+  EN_RC(abi_make_tmap_bf16(&e->s_x0, e->x0, T, kHid, 32, kBM));
+  EN_RC(abi_make_tmap_bf16(&e->s_x1, e->x1, T, kHid, 32, kBM));
+  EN_RC(abi_make_tmap_bf16(&e->s_h, e->h, T, kFfn, 32, kBM));
+  EN_RC(abi_make_tmap_bf16(&e->s_qk, e->qk, T, 2 * kHid, 32, kBM));
+  EN_RC(abi_make_tmap_bf16(&e->s_vt, e->vt, kHid, T, 64, 32));
 #undef EN_TRY
 #undef EN_RC
   *out = e;
@@ -398,7 +404,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.K = kHid;
     g.bias = L.bqkv;
     g.qscale = 1.4426950408889634f / sqrtf((float)kHeadDim);
-    CU_TRY(launch_gemm(kEpiQKV, e->sm_count, e->t_x0, L.t_wqkv, e->t_qk, e->t_vt, g, st));
+    CU_TRY(launch_gemm(kEpiQKV, e->sm_count, e->t_x0, L.t_wqkv, e->s_qk, e->s_vt, g, st));
     if ((rc = prof_mark(e, kPQkv, st))) return rc;
     AttnParams a{};
     a.qblk = e->d_qblk;
@@ -413,13 +419,13 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x0;
     g.gamma = L.ln1g;
     g.beta = L.ln1b;
-    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_ctx, L.t_wo, e->t_x1, e->t_x1, g, st));
+    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_ctx, L.t_wo, e->s_x1, e->s_x1, g, st));
     if ((rc = prof_mark(e, kPOut, st))) return rc;
     // FFN
     g.N = kFfn;
     g.K = kHid;
     g.bias = L.b1;
-    CU_TRY(launch_gemm(kEpiGelu, e->sm_count, e->t_x1, L.t_w1, e->t_h, e->t_h, g, st));
+    CU_TRY(launch_gemm(kEpiGelu, e->sm_count, e->t_x1, L.t_w1, e->s_h, e->s_h, g, st));
     if ((rc = prof_mark(e, kPUp, st))) return rc;
     g.N = kHid;
     g.K = kFfn;
@@ -427,7 +433,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x1;
     g.gamma = L.ln2g;
     g.beta = L.ln2b;
-    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->t_x0, e->t_x0, g, st));
+    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->s_x0, e->s_x0, g, st));
     if ((rc = prof_mark(e, kPDown, st))) return rc;
   }
   e->last_tokens = host_cu[n_seqs];
