@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfrs_b200.so")
+# FRS_B200_LIB: a differently-flagged build of the same library (kernel experiments, scripts/); never a fallback
+LIB_PATH = os.environ.get("FRS_B200_LIB") or os.path.join(_HERE, "csrc", "libfrs_b200.so")
 
 FRS_OK = 0
 FRS_DTYPE_F32 = 0

@@ -54,7 +54,7 @@ __device__ __forceinline__ void mbar_wait_c(uint64_t* bar, uint32_t parity, uint
 __device__ __forceinline__ void mbar_wait_bg(uint64_t* bar, uint32_t parity, uint32_t code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(FRS_BG_SLEEP_NS);
+    if (FRS_BG_SLEEP_NS > 0) __nanosleep(FRS_BG_SLEEP_NS);
     if (++spins > (1u << 22)) trap_with_code(code, parity);
   }
 }
@@ -321,7 +321,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this loop converged; the elected lane executes the tcgen05 instructions
+    // (tc_mma_f16_pred / elect.sync): descriptors stay in uniform registers and the MMAs issue back to back.
+    {
+      const uint32_t issue = elect_one_pred();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform: stays in a uniform register
       constexpr uint32_t idesc = make_idesc(1u, kBM, kNSub);
       uint32_t it = 0, lt = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
@@ -329,7 +333,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t aph = (lt / C::kAcc) & 1;
         mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_u + acc * BN;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -342,11 +346,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint64_t db = make_desc_sw128(sa + C::kStageA + s * (kNSub * 128));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              tc_mma<false>(d_tmem + s * kNSub, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0));
+              tc_mma_f16_pred(d_tmem + s * kNSub, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
           }
-          tc_commit(&empty[stage]);
+          tc_commit_pred(&empty[stage], issue);
         }
-        tc_commit(&tfull[acc]);
+        tc_commit_pred(&tfull[acc], issue);
       }
     }
   } else {
@@ -564,6 +568,14 @@ struct AttnSmem {
   static constexpr int total = holder + 16;
 };
 
+// -DFRS_ATTN_TRACE: event timeline (clock64 << 8 | event id) of CTA 0: role 0 = MMA issuer, role 1 / 2 = lane 0 of
+// the first softmax warp of head 0 / head 1 (launch_attention dumps it to gpurun_out/attn_trace.txt)
+#ifdef FRS_ATTN_TRACE
+constexpr int kTraceCap = 4096;
+#define FRS_TR(id) do { if (tr && trn < kTraceCap) tr[trn++] = (clock64() << 8) | (long long)(id); } while (0)
+#else
+#define FRS_TR(id) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
                  const AttnParams p) {
@@ -636,7 +648,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this loop converged; only lane 0 executes the tcgen05 instructions (see
+    // tc_mma_f16_pred): inside an `if (lane == 0)` region every MMA cost ~70 clk of R2UR/ELECT loops and
+    // the issue of one block's P.V MMAs (555 clk) sat on the softmax warps' critical path.
+    {
+      const uint32_t issue = elect_one_pred();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform: stays in a uniform register
+#ifdef FRS_ATTN_TRACE
+      long long* tr = (p.timing && blockIdx.x == 0 && issue) ? p.timing + 64 : nullptr;
+      int trn = 0;
+#endif
       constexpr uint32_t idesc_s = make_idesc(1u, kBM, kKB);        // S = Q K^T : 128 x 128
       constexpr uint32_t idesc_o = make_idesc(1u, kBM, kHeadDim);   // O = P V   : 128 x 32
       // Two cursors over this CTA's (item, key block) sequence: the score MMAs run one block AHEAD of
@@ -649,7 +670,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       auto load_item = [&](Cursor& c) {
         if (c.item < n_items) {
           const QBlock qb = p.qblk[c.item / kHeadPairs];
-          c.nkb = (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB;
+          // (a loaded value is not provably warp-uniform; the shuffle makes the loop control uniform again)
+          c.nkb = __shfl_sync(0xffffffffu, (qb.seq_tok0 - qb.kv_tok0 + qb.seq_len + kKB - 1) / kKB, 0);
         }
       };
       auto advance = [&](Cursor& c) {
@@ -672,11 +694,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         for (int h = 0; h < 2; ++h) {
           mbar_wait_bg(&s_free[h], (c.g & 1) ^ 1, 109u);  // softmax warps hold the previous S of this head in registers
           tc_fence_after();
+          FRS_TR(1 + h);
           const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
           const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
-          tc_mma<false>(tmem_base + kTmemS + 128 * h, da, db, idesc_s, 0u);
-          tc_mma<false>(tmem_base + kTmemS + 128 * h, da + 2, db + 2, idesc_s, 1u);
-          tc_commit(&s_full[h]);
+          tc_mma_f16_pred(tmem_u + kTmemS + 128 * h, da, db, idesc_s, 0u, issue);
+          tc_mma_f16_pred(tmem_u + kTmemS + 128 * h, da + 2, db + 2, idesc_s, 1u, issue);
+          tc_commit_pred(&s_full[h], issue);
+          FRS_TR(3 + h);
         }
       };
       Cursor cs{(int)blockIdx.x, 0, 0, 0u, 0u}, cp{(int)blockIdx.x, 0, 0, 0u, 0u};
@@ -697,18 +721,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         for (int h = 0; h < 2; ++h) {
           mbar_wait_bg(&p_full[h], cp.g & 1, 110u);  // P of this block is in tensor memory, previous O block was read
           tc_fence_after();
+          FRS_TR(5 + h);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)  // 16 keys per MMA = 8 columns of packed bf16 pairs
-              tc_mma_ts(tmem_base + kTmemO + 32 * h, tmem_base + kTmemP + 64 * h + (s * 4 + kk) * 8, db + 2 * kk, idesc_o,
-                        (uint32_t)((s | kk) != 0));
+              tc_mma_ts_pred(tmem_u + kTmemO + 32 * h, tmem_u + kTmemP + 64 * h + (s * 4 + kk) * 8, db + 2 * kk,
+                             idesc_o, (uint32_t)((cp.kb | s | kk) != 0), issue);
           }
-          tc_commit(&o_full[h]);
+          tc_commit_pred(&o_full[h], issue);
+          FRS_TR(7 + h);
         }
-        tc_commit(&kv_empty[stage]);
-        if (cp.kb == cp.nkb - 1) tc_commit(&q_empty[cp.li & 1]);
+        tc_commit_pred(&kv_empty[stage], issue);
+        if (cp.kb == cp.nkb - 1) tc_commit_pred(&q_empty[cp.li & 1], issue);
         advance(cp);
       }
     }
@@ -723,6 +749,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     const uint32_t t_o = tmem_base + ((quarter * 32u) << 16) + kTmemO + 32 * h;
     const uint32_t t_p = tmem_base + ((quarter * 32u) << 16) + kTmemP + 64 * h;
     uint32_t g = 0;
+#ifdef FRS_ATTN_TRACE
+    long long* tr = (p.timing && blockIdx.x == 0 && quarter == 0 && lane == 0) ? p.timing + 64 + (1 + h) * kTraceCap : nullptr;
+    int trn = 0;
+#endif
     // -DFRS_ATTN_TIMING: per-phase clock sums of the softmax warps of CTA 0 (printed by launch_attention)
 #ifdef FRS_ATTN_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -730,15 +760,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
 #else
 #define FRS_T(i) do { } while (0)
 #endif
+    // O stays in TENSOR MEMORY for the whole item: the P.V MMAs of key blocks 1.. accumulate onto block 0's, and
+    // a thread only touches O (a) at the end of the item and (b) when its running reference maximum has to move.
+    // The reference moves lazily: softmax is invariant to the reference m as long as 2^(s - m) stays finite, so
+    // a row keeps the reference of its first block until a later block exceeds it by more than 2^kLazyLog2
+    // (P <= 256 is exact in bf16's range; its relative rounding does not depend on the scale).  Per block this
+    // removes the O read, 64 FP32 ops and 32 registers per thread that the register-resident O cost.
+    //
+    // The output of an item (last O + normalisation + stores) is written while the FIRST block of the next item
+    // is in flight: its P.V round trip and the QBlock fetch of the next item (prefetched one item ahead) used
+    // to sit between two items with the MUFU idle.
+    constexpr float kLazyLog2 = 8.0f;
+    float m = -INFINITY, l = 0.f;
+    QBlock qb_next = p.qblk[(blockIdx.x < n_items ? blockIdx.x : 0) / kHeadPairs];
+    __nv_bfloat16* dst_prev = nullptr;  // context row of this thread in the item being accumulated (null: padding row)
+    // writes the context row of the item that ended with block g - 1 (its accumulated O is in TMEM)
+    auto flush_item = [&]() {
+      mbar_wait_c(&o_full[h], (g - 1) & 1, 113u);
+      tc_fence_after();
+      FRS_TR(19);
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_o + 16 * half, v);
+        tmem_ld_wait();
+        if (dst_prev != nullptr) {
+          uint32_t ok[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ok[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+          uint4* dst = reinterpret_cast<uint4*>(dst_prev) + 2 * half;
+          dst[0] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+          dst[1] = make_uint4(ok[4], ok[5], ok[6], ok[7]);
+        }
+      }
+      FRS_T(7);
+      FRS_TR(20);
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const QBlock qb = p.qblk[item / kHeadPairs];
+      const QBlock qb = qb_next;
+      if (item + (int)gridDim.x < n_items) qb_next = p.qblk[(item + gridDim.x) / kHeadPairs];
       const int hp = item % kHeadPairs;
       const int key_off = qb.seq_tok0 - qb.kv_tok0;  // keys of the first block before the sequence (< 8)
       const int nkb = (key_off + qb.seq_len + kKB - 1) / kKB;
-      float m = -INFINITY, l = 0.f;
-      float o[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = 0.f;
       uint32_t s0[32], s1[32], s2[32], s3[32];  // one score row of the block: a single pass over TMEM
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         // keys [lo, hi) of this block belong to the sequence (hi - lo >= 1)
@@ -746,9 +811,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const int hi = min(kKB, key_off + qb.seq_len - kb * kKB);
         const bool full = lo == 0 && hi == kKB;
         FRS_T(0);
+        FRS_TR(10);
         mbar_wait_c(&s_full[h], g & 1, 111u);
         tc_fence_after();
         FRS_T(1);
+        FRS_TR(11);
         tmem_ld_32x32(t_s, s0);
         tmem_ld_32x32(t_s + 32, s1);
         tmem_ld_32x32(t_s + 64, s2);
@@ -759,6 +826,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[h]);
         FRS_T(2);
+        FRS_TR(12);
         if (!full) {
           auto mask = [&](uint32_t(&sv)[32], int c) {
 #pragma unroll
@@ -773,44 +841,73 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         // block maximum (scores are already in the log2 domain: q was scaled by log2e/sqrt(32))
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          mx0 = fmaxf(mx0, __uint_as_float(s0[j]));
-          mx1 = fmaxf(mx1, __uint_as_float(s1[j]));
-          mx2 = fmaxf(mx2, __uint_as_float(s2[j]));
-          mx3 = fmaxf(mx3, __uint_as_float(s3[j]));
+        for (int j = 0; j < 32; j += 2) {  // FMNMX3: two scores per instruction
+          mx0 = fmax3(mx0, __uint_as_float(s0[j]), __uint_as_float(s0[j + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s1[j]), __uint_as_float(s1[j + 1]));
+          mx2 = fmax3(mx2, __uint_as_float(s2[j]), __uint_as_float(s2[j + 1]));
+          mx3 = fmax3(mx3, __uint_as_float(s3[j]), __uint_as_float(s3[j + 1]));
         }
-        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-        const float alpha = ex2_approx(m - m_new);  // 0 on the first block (m = -inf)
+        const float bm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         FRS_T(3);
-        if (kb > 0) {
-          // previous P.V finished: its O block is ready and P may be overwritten
-          mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
-          tc_fence_after();
-          FRS_T(4);
-          uint32_t ob[32];
-          tmem_ld_32x32(t_o, ob);
-          tmem_ld_wait();
+        FRS_TR(13);
+        bool pv_done = g == 0;  // P.V of block g - 1 is known to have finished (its P buffer may be overwritten)
+        if (kb == 0) {
+          if (g > 0) {
+            flush_item();  // previous item of this CTA
+            pv_done = true;
+          }
+          m = bm;
+          l = 0.f;
+          const int qi = qb.q_tok0 - qb.seq_tok0 + (int)row;  // position of this query in its sequence
+          dst_prev = qi < qb.seq_len ? p.ctx + (size_t)(qb.q_tok0 + row) * kHid + (hp * 2 + h) * kHeadDim : nullptr;
+        } else {
+          const bool move = bm > m + kLazyLog2;
+          if (__any_sync(0xffffffffu, move)) {
+            // rare: rescale this row's O (and l) to the new reference; rows that keep theirs multiply by 1
+            const float m_new = move ? bm : m;
+            const float alpha = ex2_approx(m - m_new);
+            mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
+            tc_fence_after();
+            pv_done = true;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = (o[j] + __uint_as_float(ob[j])) * alpha;
-          l *= alpha;
+            for (int half = 0; half < 2; ++half) {
+              uint32_t v[16];
+              tmem_ld_32x16(t_o + 16 * half, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+              tmem_st_32x16(t_o + 16 * half, v);
+            }
+            tmem_st_wait();
+            l *= alpha;
+            m = m_new;
+          }
         }
-        m = m_new;
         FRS_T(5);
+        FRS_TR(15);
         // p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V); masked keys give 0.
         // P goes straight back to tensor memory as the A operand of P.V: key k of this row = half (k & 1) of
         // column k / 2.  It never touches shared memory.
         float ps0 = 0.f, ps1 = 0.f;
         uint32_t pw0[32], pw1[32];  // two buffers: the asynchronous TMEM store of the first may still read it
+#ifndef FRS_ATTN_NO_TURNS
+        // The two warps of a sub-partition (same quarter, head 0 / head 1) share one MUFU unit.  Left alone
+        // they run in lockstep (both are released by the same score MMAs): both exponentiate at half rate,
+        // then both leave the unit idle.  They take turns instead, so that the exp pass of one head overlaps
+        // the load / max phases of the other.  The float operand ties the barrier into the data flow: no exp
+        // may be scheduled above it.
+        if (h == 0) {
+          if (g > 0) asm volatile("bar.sync %1, 64;" : "+f"(m) : "r"(5u + quarter) : "memory");
+        } else {
+          asm volatile("bar.sync %1, 64;" : "+f"(m) : "r"(1u + quarter) : "memory");
+        }
+#endif
+        FRS_TR(16);
         auto expo = [&](uint32_t(&sv)[32], uint32_t(&pw)[32], int half) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-#ifdef FRS_ATTN_NOEXP_H1  // measurement only: head 1 skips the MUFU (wrong results) to expose MUFU sharing
-            const float a = h ? (__uint_as_float(sv[2 * j]) - m) * 0.001f : ex2_approx(__uint_as_float(sv[2 * j]) - m);
-            const float b = h ? (__uint_as_float(sv[2 * j + 1]) - m) * 0.001f : ex2_approx(__uint_as_float(sv[2 * j + 1]) - m);
-#else
             const float a = ex2_approx(__uint_as_float(sv[2 * j]) - m);
             const float b = ex2_approx(__uint_as_float(sv[2 * j + 1]) - m);
-#endif
             ps0 += a;
             ps1 += b;
             pw[half * 16 + j] = pack_bf16x2(a, b);
@@ -818,39 +915,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         };
         expo(s0, pw0, 0);
         expo(s1, pw0, 1);
+        if (!pv_done) {
+          // P.V of the previous block reads the P buffer this block overwrites (it finished long ago)
+          mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
+          tc_fence_after();
+        }
         tmem_st_32x32(t_p, pw0);
         expo(s2, pw1, 0);
         expo(s3, pw1, 1);
         tmem_st_32x32(t_p + 32, pw1);
+#ifndef FRS_ATTN_NO_TURNS
+        asm volatile("bar.arrive %2, 64;" : "+f"(ps0), "+f"(ps1) : "r"((h == 0 ? 1u : 5u) + quarter) : "memory");
+#endif
+        FRS_TR(17);
         l += ps0 + ps1;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[h]);
         FRS_T(6);
+        FRS_TR(18);
       }
-      // last O block, normalise, write the context rows of this head
-      mbar_wait_c(&o_full[h], (g - 1) & 1, 113u);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(t_o, v);
-      tmem_ld_wait();
-      const int qi = qb.q_tok0 - qb.seq_tok0 + (int)row;  // position of this query in its sequence
-      if (qi < qb.seq_len) {
-        const float inv = 1.0f / l;
-        uint32_t ok[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          ok[j] = pack_bf16x2((o[2 * j] + __uint_as_float(v[2 * j])) * inv,
-                              (o[2 * j + 1] + __uint_as_float(v[2 * j + 1])) * inv);
-        uint4* dst = reinterpret_cast<uint4*>(p.ctx + (size_t)(qb.q_tok0 + row) * kHid + (hp * 2 + h) * kHeadDim);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ok[4 * j], ok[4 * j + 1], ok[4 * j + 2], ok[4 * j + 3]);
-      }
-      // the O block of this item has been read: the next item's first P.V may overwrite it only after
-      // this warp arrives on p_full again, which happens after this point (program order)
-      FRS_T(7);
     }
+    if (g > 0) flush_item();
+#ifndef FRS_ATTN_NO_TURNS
+    if (h == 0 && g > 0) named_bar_sync(5u + quarter, 64);  // consume the last turn of head 1
+#endif
 #ifdef FRS_ATTN_TIMING
     if (p.timing && lane == 0 && blockIdx.x == 0)
       for (int i = 0; i < 8; ++i) p.timing[(warp - 4) * 8 + i] = tacc[i];
@@ -1029,6 +1119,29 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   const int items = p.nqb * kHeadPairs;
   if (items <= 0) return cudaSuccess;
   const int grid = items < sm_count ? items : sm_count;
+#ifdef FRS_ATTN_TRACE
+  {
+    static long long* th = nullptr;
+    static int calls = 0;
+    const int n = 64 + 3 * kTraceCap;
+    if (!th) cudaHostAlloc(&th, n * 8, cudaHostAllocMapped);
+    memset(th, 0, n * 8);
+    AttnParams pd = p;
+    cudaHostGetDevicePointer(&pd.timing, th, 0);
+    attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, pd);
+    cudaStreamSynchronize(st);
+    if (++calls == 30) {
+      FILE* f = fopen("gpurun_out/attn_trace.txt", "w");
+      if (f) {
+        for (int r = 0; r < 3; ++r)
+          for (int i = 0; i < kTraceCap && th[64 + r * kTraceCap + i]; ++i)
+            fprintf(f, "%d %lld %lld\n", r, th[64 + r * kTraceCap + i] >> 8, th[64 + r * kTraceCap + i] & 255);
+        fclose(f);
+      }
+    }
+    return cudaGetLastError();
+  }
+#endif
 #ifdef FRS_ATTN_TIMING
   static long long* th = nullptr;
   static int calls = 0;

@@ -302,6 +302,55 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
       : "memory");
 }
 
+// 1 in exactly one lane of the (converged) warp, chosen by the hardware: elect.sync
+__device__ __forceinline__ uint32_t elect_one_pred() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+// Predicated forms for an issuer WARP that stays converged: every lane runs the (uniform) control flow and
+// address arithmetic — so the compiler keeps descriptors in uniform registers instead of the
+// ELECT / R2UR.BROADCAST loops it emits inside an `if (lane == 0)` region (~70 clk per MMA) — and only the
+// lane with issue != 0 executes the instruction.
+__device__ __forceinline__ void tc_mma_f16_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane
 // (lane_base + i); lane_base must be 32 * (warp_id % 4).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -356,6 +405,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
       "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
       "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
       "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
