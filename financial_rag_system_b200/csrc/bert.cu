@@ -260,6 +260,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   constexpr bool kPair = EPI == kEpiResLN;  // 2-CTA cluster, one column half each
+  constexpr int kResSteps = BN / 64;        // ResLN: K-steps that add the residual (see the producer)
+  constexpr int kEyeOff = 2 * kChunkBox;    // ResLN: identity tile inside the staging area
+  constexpr uint32_t kBoxRing = kPair ? 2 : 3;  // staging boxes per column group
   const int nt_count = kPair ? 1 : p.N / BN;
   const int ksteps = p.K / 64;
   const int num_tiles = p.num_mtiles * nt_count;
@@ -286,6 +289,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       sgamma[i] = p.gamma[i];
       sbeta[i] = p.beta[i];
     }
+  }
+  if constexpr (kPair) {
+    // I64: a 64 x 64 bf16 identity as a K-major SWIZZLE_128B operand tile (the B operand of the residual
+    // K-steps), in the third staging box of column group 0 (ResLN rings two boxes per group)
+    uint8_t* eye = sout0 + kEyeOff;
+    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {  // 16-byte chunk (n, c): columns 8c .. 8c+7 of row n
+      const int n = i >> 3, c = i & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c == (n >> 3)) {
+        const uint32_t one = 0x3F80u << (16 * (n & 1));
+        const int w = (n & 7) >> 1;
+        v.x = w == 0 ? one : 0u;
+        v.y = w == 1 ? one : 0u;
+        v.z = w == 2 ? one : 0u;
+        v.w = w == 3 ? one : 0u;
+      }
+      *reinterpret_cast<uint4*>(eye + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+    }
+    fence_proxy_async();
   }
   if (warp == 1) {
     tmem_alloc(holder, 512);
@@ -316,6 +338,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int s = 0; s < C::kNSplit; ++s)
             tma_load_2d(sa + C::kStageA + s * (kNSub * 128), &tmap_b, &full[stage], ks * 64,
                         nt * BN + s * kNSub, kEvictLast);
+        }
+        if constexpr (kPair) {
+          // the residual rides through the tensor core: three more K-steps whose A slab is the residual's
+          // [128 rows x 64 columns] of this CTA's column half (tmap_out2 = the residual as an A operand)
+          for (int r = 0; r < kResSteps; ++r, ++it) {
+            const uint32_t stage = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1;
+            mbar_wait_c(&empty[stage], ph ^ 1, 101u);
+            mbar_arrive_expect_tx(&full[stage], C::kStageA);
+            tma_load_2d(ring + (size_t)stage * C::kStage, &tmap_out2, &full[stage], nt * BN + r * 64, mt * kBM, kEvictNormal);
+          }
         }
       }
     }
@@ -350,6 +383,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           tc_commit_pred(&empty[stage], issue);
         }
+        if constexpr (kPair) {
+          // acc[:, 64 r .. 64 r + 64) += residual slab . I64^T  (bf16 x 1.0 accumulated in fp32: exact)
+          constexpr uint32_t idesc_eye = make_idesc(1u, kBM, 64);
+          const uint64_t deye = make_desc_sw128(smem_u32(sout0 + kEyeOff));
+          for (int r = 0; r < kResSteps; ++r, ++it) {
+            const uint32_t stage = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1;
+            mbar_wait_c(&full[stage], ph, 103u);
+            tc_fence_after();
+            const uint64_t da = make_desc_sw128(smem_u32(ring + (size_t)stage * C::kStage));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_f16_pred(d_tmem + r * 64, da + 2 * kk, deye + 2 * kk, idesc_eye, 1u, issue);
+            tc_commit_pred(&empty[stage], issue);
+          }
+        }
         tc_commit_pred(&tfull[acc], issue);
       }
     }
@@ -367,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     // stage 32 columns (packed bf16 pairs o[16]) of this thread's row, then store the box [128 rows x 32 cols]
     auto stage_and_store = [&](const uint32_t (&o)[16], int col, int mt) {
-      uint8_t* box = sgroup + (nchunk % 3) * kChunkBox;
+      uint8_t* box = sgroup + (nchunk % kBoxRing) * kChunkBox;
       uint8_t* dst = box + row * 64;  // SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -389,14 +438,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t aph = (lt / C::kAcc) & 1;
       const int grow = mt * kBM + (int)row;
       const bool live = grow < p.M;
-      // ResLN: this thread's 192 residual values are fetched BEFORE the accumulator is waited for, so
-      // their global-memory latency hides behind the tile's MMA main loop
-      uint4 rres[EPI == kEpiResLN ? C::kColsPerThread / 8 : 1];
-      if constexpr (EPI == kEpiResLN) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)grow * kHid + nt * BN + half * C::kColsPerThread);
-#pragma unroll
-        for (int j = 0; j < C::kColsPerThread / 8; ++j) rres[j] = live ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
-      }
       mbar_wait_c(&tfull[acc], aph, 104u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN + half * C::kColsPerThread;
@@ -459,23 +500,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       } else {
-        // bias + residual, row statistics of this CTA's 192 columns; the pre-LayerNorm value goes back to
-        // TMEM (fp32)
+        // bias (+ the residual, which the last three K-steps added to the accumulator), row statistics of this
+        // CTA's 192 columns; the pre-LayerNorm value goes back to TMEM (fp32)
         float sum = 0.f, sq = 0.f;
 #pragma unroll
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
           const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          const uint32_t rw[16] = {rres[4 * c].x,     rres[4 * c].y,     rres[4 * c].z,     rres[4 * c].w,
-                                   rres[4 * c + 1].x, rres[4 * c + 1].y, rres[4 * c + 1].z, rres[4 * c + 1].w,
-                                   rres[4 * c + 2].x, rres[4 * c + 2].y, rres[4 * c + 2].z, rres[4 * c + 2].w,
-                                   rres[4 * c + 3].x, rres[4 * c + 3].y, rres[4 * c + 3].z, rres[4 * c + 3].w};
           const float* bs = sbias + col;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(v[2 * j]) + bs[2 * j] + bf16_lo(rw[j]);
-            const float b = __uint_as_float(v[2 * j + 1]) + bs[2 * j + 1] + bf16_hi(rw[j]);
+            const float a = __uint_as_float(v[2 * j]) + bs[2 * j];  // the residual is already in the accumulator
+            const float b = __uint_as_float(v[2 * j + 1]) + bs[2 * j + 1];
             sum += a + b;
             sq += a * a + b * b;
             v[2 * j] = __float_as_uint(a);
@@ -883,6 +920,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
             m = m_new;
           }
         }
+        if (!pv_done) {
+          // P.V of the previous block reads the P buffer this block overwrites; it finished while this warp
+          // loaded S and took the maximum, and the check stays outside the exp pass (the other head waits for its end)
+          mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
+          tc_fence_after();
+        }
         FRS_T(5);
         FRS_TR(15);
         // p = 2^(s - m), rounded to bf16 (the value the tensor core multiplies with V); masked keys give 0.
@@ -903,26 +946,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         }
 #endif
         FRS_TR(16);
-        auto expo = [&](uint32_t(&sv)[32], uint32_t(&pw)[32], int half) {
+        // One software-pipelined pass over the 64 score pairs: the row sums and the bf16 packing of pair
+        // j - kExpLag are issued behind the exponentials of pair j.  (Written pair by pair, ptxas put each
+        // FADD2 of the row sum right behind the two MUFUs it consumes: the warp stalled ~10 clk per pair on
+        // the MUFU latency and an exclusive pass took 1600 clk instead of 128 x 8.)
+        constexpr int kExpLag = 6;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = ex2_approx(__uint_as_float(sv[2 * j]) - m);
-            const float b = ex2_approx(__uint_as_float(sv[2 * j + 1]) - m);
-            ps0 += a;
-            ps1 += b;
-            pw[half * 16 + j] = pack_bf16x2(a, b);
+        for (int j = 0; j < 64 + kExpLag; ++j) {
+          if (j < 64) {
+            uint32_t(&sv)[32] = j < 16 ? s0 : j < 32 ? s1 : j < 48 ? s2 : s3;
+            const int i = (j & 15) * 2;
+            float a = __uint_as_float(sv[i]), b = __uint_as_float(sv[i + 1]);
+            fadd2(a, b, -m, -m);  // FADD2: one issue slot per score pair
+            sv[i] = __float_as_uint(ex2_approx(a));
+            sv[i + 1] = __float_as_uint(ex2_approx(b));
           }
-        };
-        expo(s0, pw0, 0);
-        expo(s1, pw0, 1);
-        if (!pv_done) {
-          // P.V of the previous block reads the P buffer this block overwrites (it finished long ago)
-          mbar_wait_c(&o_full[h], (g - 1) & 1, 112u);
-          tc_fence_after();
+          if (j >= kExpLag) {
+            const int jj = j - kExpLag;
+            uint32_t(&sv)[32] = jj < 16 ? s0 : jj < 32 ? s1 : jj < 48 ? s2 : s3;
+            const int i = (jj & 15) * 2;
+            const float a = __uint_as_float(sv[i]), b = __uint_as_float(sv[i + 1]);
+            fadd2(ps0, ps1, a, b);
+            (jj < 32 ? pw0 : pw1)[jj & 31] = pack_bf16x2(a, b);
+            if (jj == 31) tmem_st_32x32(t_p, pw0);
+          }
         }
-        tmem_st_32x32(t_p, pw0);
-        expo(s2, pw1, 0);
-        expo(s3, pw1, 1);
         tmem_st_32x32(t_p + 32, pw1);
 #ifndef FRS_ATTN_NO_TURNS
         asm volatile("bar.arrive %2, 64;" : "+f"(ps0), "+f"(ps1) : "r"((h == 0 ? 1u : 5u) + quarter) : "memory");

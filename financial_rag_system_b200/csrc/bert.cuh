@@ -80,7 +80,7 @@ cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const i
 // tmap_b: weights, box 64 x 192, SWIZZLE_128B.  Outputs leave through TMA stores:
 //   QKV    tmap_out  = qk [rows, 768], box 32 x 128 SWIZZLE_64B;  tmap_out2 = vt [384, rows], box 64 x 32 SWIZZLE_128B
 //   GELU   tmap_out  = h [rows, 1536], box 32 x 128 SWIZZLE_64B   (tmap_out2 unused)
-//   ResLN  tmap_out  = x [rows, 384],  box 32 x 128 SWIZZLE_64B   (tmap_out2 unused)
+//   ResLN  tmap_out  = x [rows, 384],  box 32 x 128 SWIZZLE_64B;  tmap_out2 = the RESIDUAL as an A operand (box 64 x 128 SWIZZLE_128B)
 cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
                         const CUtensorMap& tmap_out, const CUtensorMap& tmap_out2, const GemmParams& p,
                         cudaStream_t st);

@@ -344,6 +344,16 @@ __device__ __forceinline__ void tc_commit_pred(uint64_t* bar, uint32_t issue) {
       "r"(issue)
       : "memory");
 }
+// packed fp32 pair add (one FADD2 on sm_100): (a, b) += (c, d)
+__device__ __forceinline__ void fadd2(float& a, float& b, float c, float d) {
+  asm("{\n\t.reg .b64 x, y;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %3};\n\t"
+      "add.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b)
+      : "f"(c), "f"(d));
+}
 // three-input maximum (one FMNMX3 on sm_100)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;

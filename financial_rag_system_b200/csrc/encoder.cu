@@ -419,7 +419,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x0;
     g.gamma = L.ln1g;
     g.beta = L.ln1b;
-    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_ctx, L.t_wo, e->s_x1, e->s_x1, g, st));
+    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_ctx, L.t_wo, e->s_x1, e->t_x0, g, st));
     if ((rc = prof_mark(e, kPOut, st))) return rc;
     // FFN
     g.N = kFfn;
@@ -433,7 +433,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x1;
     g.gamma = L.ln2g;
     g.beta = L.ln2b;
-    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->s_x0, e->s_x0, g, st));
+    CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->s_x0, e->t_x1, g, st));
     if ((rc = prof_mark(e, kPDown, st))) return rc;
   }
   e->last_tokens = host_cu[n_seqs];
