@@ -115,6 +115,27 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, tanh_approx(x * u), hx);
 #endif
 }
+// two elements at once on the packed fp32 pipes (FMUL2 / FFMA2): 7 packed ops + 2 MUFU per pair instead of
+// 16 + 2 — the GELU epilogue is issue-bound (bit-identical to gelu_erf: same operations, same rounding)
+__device__ __forceinline__ void gelu_erf2(float& a, float& b) {
+#ifdef FRS_EXACT_GELU
+  a = gelu_erf(a);
+  b = gelu_erf(b);
+#else
+  float x2a = a, x2b = b;
+  fmul2(x2a, x2b, a, b);                                                  // x^2
+  float ua = x2a, ub = x2b;
+  ffma2(ua, ub, -0.00035151678934123415f, -0.00035151678934123415f, 0.03700564602521096f, 0.03700564602521096f);
+  ffma2(ua, ub, x2a, x2b, 0.7975078842799184f, 0.7975078842799184f);      // c0 + x^2 (c1 + c2 x^2)
+  fmul2(ua, ub, a, b);                                                    // x u
+  ua = tanh_approx(ua);
+  ub = tanh_approx(ub);
+  fmul2(a, b, 0.5f, 0.5f);                                                // x / 2
+  ffma2(ua, ub, a, b, a, b);                                              // (x/2) t + x/2
+  a = ua;
+  b = ub;
+#endif
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -236,6 +257,14 @@ constexpr int kChunkBox = kBM * 64;  // 128 rows x 32 bf16
 // the epilogue overlaps the next tile's MMAs (a 384-column accumulator cannot be double-buffered in 512
 // TMEM columns).  The halves exchange their per-row (sum, sum of squares) through distributed shared
 // memory: every epilogue thread stores its partial into the peer CTA and arrives on the peer's mbarrier.
+// -DFRS_GEMM_TRACE: event timeline (clock64 << 8 | id) of CTA 0 of one launch: role 0 = MMA issuer, role 1 = lane 0
+// of the first epilogue warp, role 2 = TMA producer (dumped to gpurun_out/gemm_trace_<epi>.txt)
+#ifdef FRS_GEMM_TRACE
+constexpr int kGTraceCap = 4096;
+#define FRS_GT(id) do { if (gtr && gtn < kGTraceCap) gtr[gtn++] = (clock64() << 8) | (long long)(id); } while (0)
+#else
+#define FRS_GT(id) do { } while (0)
+#endif
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -261,8 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t lane = threadIdx.x & 31;
   constexpr bool kPair = EPI == kEpiResLN;  // 2-CTA cluster, one column half each
   constexpr int kResSteps = BN / 64;        // ResLN: K-steps that add the residual (see the producer)
-  constexpr int kEyeOff = 2 * kChunkBox;    // ResLN: identity tile inside the staging area
-  constexpr uint32_t kBoxRing = kPair ? 2 : 3;  // staging boxes per column group
+  constexpr int kEyeOff = 2048;             // ResLN: identity tile, byte offset inside the bias area (floats 512..1023)
   const int nt_count = kPair ? 1 : p.N / BN;
   const int ksteps = p.K / 64;
   const int num_tiles = p.num_mtiles * nt_count;
@@ -291,10 +319,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   }
   if constexpr (kPair) {
-    // I64: a 64 x 64 bf16 identity as a K-major SWIZZLE_128B operand tile (the B operand of the residual
-    // K-steps), in the third staging box of column group 0 (ResLN rings two boxes per group)
-    uint8_t* eye = sout0 + kEyeOff;
-    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {  // 16-byte chunk (n, c): columns 8c .. 8c+7 of row n
+    // I16: a 16 x 16 bf16 identity as a K-major SWIZZLE_128B operand tile (16 rows x 128 B, columns 0..15 used):
+    // the B operand of the residual MMAs.  It lives in the part of the bias area a 384-wide GEMM does not use.
+    uint8_t* eye = sm + C::kParF + kEyeOff;
+    for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {  // 16-byte chunk (n, c): columns 8c .. 8c+7 of row n
       const int n = i >> 3, c = i & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (c == (n >> 3)) {
@@ -324,6 +352,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
+#ifdef FRS_GEMM_TRACE
+      long long* gtr = (p.trace && blockIdx.x == 0) ? p.trace + 2 * kGTraceCap : nullptr;
+      int gtn = 0;
+#endif
       uint32_t it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
@@ -331,6 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait_c(&empty[stage], ph ^ 1, 101u);
+          FRS_GT(30);
           mbar_arrive_expect_tx(&full[stage], C::kStage);
           uint8_t* sa = ring + (size_t)stage * C::kStage;
           tma_load_2d(sa, &tmap_a, &full[stage], ks * 64, mt * kBM, kEvictNormal);
@@ -360,18 +393,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t issue = elect_one_pred();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform: stays in a uniform register
       constexpr uint32_t idesc = make_idesc(1u, kBM, kNSub);
+#ifdef FRS_GEMM_TRACE
+      long long* gtr = (p.trace && blockIdx.x == 0 && issue) ? p.trace : nullptr;
+      int gtn = 0;
+#endif
       uint32_t it = 0, lt = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
         const uint32_t acc = lt % C::kAcc;
         const uint32_t aph = (lt / C::kAcc) & 1;
+        FRS_GT(1);
         mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
         tc_fence_after();
+        FRS_GT(2);
         const uint32_t d_tmem = tmem_u + acc * BN;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait_c(&full[stage], ph, 103u);
           tc_fence_after();
+          FRS_GT(3);
           const uint32_t sa = smem_u32(ring + (size_t)stage * C::kStage);
           const uint64_t da = make_desc_sw128(sa);
 #pragma unroll
@@ -384,9 +424,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc_commit_pred(&empty[stage], issue);
         }
         if constexpr (kPair) {
-          // acc[:, 64 r .. 64 r + 64) += residual slab . I64^T  (bf16 x 1.0 accumulated in fp32: exact)
-          constexpr uint32_t idesc_eye = make_idesc(1u, kBM, 64);
-          const uint64_t deye = make_desc_sw128(smem_u32(sout0 + kEyeOff));
+          // acc[:, 64 r + 16 kk .. + 16) += residual columns [16 kk, +16) . I16^T  (bf16 x 1.0 accumulated in fp32: exact)
+          constexpr uint32_t idesc_eye = make_idesc(1u, kBM, 16);
+          const uint64_t deye = make_desc_sw128(smem_u32(sm + C::kParF + kEyeOff));
           for (int r = 0; r < kResSteps; ++r, ++it) {
             const uint32_t stage = it % C::kStages;
             const uint32_t ph = (it / C::kStages) & 1;
@@ -395,11 +435,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint64_t da = make_desc_sw128(smem_u32(ring + (size_t)stage * C::kStage));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              tc_mma_f16_pred(d_tmem + r * 64, da + 2 * kk, deye + 2 * kk, idesc_eye, 1u, issue);
+              tc_mma_f16_pred(d_tmem + r * 64 + kk * 16, da + 2 * kk, deye, idesc_eye, 1u, issue);
             tc_commit_pred(&empty[stage], issue);
           }
         }
         tc_commit_pred(&tfull[acc], issue);
+        FRS_GT(4);
       }
     }
   } else {
@@ -409,26 +450,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t row = quarter * 32 + lane;    // row within the tile
     const bool issuer = (threadIdx.x & 127) == 64;  // first thread of each column-half group owns its TMA stores
     uint8_t* const sgroup = sout0 + half * (3 * kChunkBox);
-    uint32_t nchunk = 0;                         // chunks staged so far by this group (ring position)
     if (issuer) {
       tma_prefetch_desc(&tmap_out);
       if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
     }
-    // stage 32 columns (packed bf16 pairs o[16]) of this thread's row, then store the box [128 rows x 32 cols]
+    uint32_t nchunk = 0;  // chunks staged so far by this group (ring position)
+#ifdef FRS_GEMM_TRACE
+    long long* gtr = (p.trace && blockIdx.x == 0 && threadIdx.x == 64) ? p.trace + kGTraceCap : nullptr;
+    int gtn = 0;
+#endif
+    // stage 32 columns (packed bf16 pairs o[16]) of this thread's row, then store the box [128 rows x 32 cols].
+    // (Staging the whole half tile and storing its three boxes behind one barrier measured 5 % SLOWER: the
+    // chunk-by-chunk stores overlap the rest of the tile's epilogue.)
     auto stage_and_store = [&](const uint32_t (&o)[16], int col, int mt) {
-      uint8_t* box = sgroup + (nchunk % kBoxRing) * kChunkBox;
+      uint8_t* box = sgroup + (nchunk % 3) * kChunkBox;
       uint8_t* dst = box + row * 64;  // SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(dst + ((j ^ ((row >> 1) & 3)) << 4)) =
             make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      FRS_GT(13);
       fence_proxy_async();
       named_bar_sync(2 + half, 128);
+      FRS_GT(14);
       if (issuer) {
         tma_store_2d(&tmap_out, box, col, mt * kBM);
         tma_store_commit();
         tma_store_wait_read<1>();  // the store issued one chunk ago has left shared memory
       }
+      FRS_GT(15);
       ++nchunk;
     };
     uint32_t lt = 0;
@@ -436,10 +486,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
       const uint32_t acc = lt % C::kAcc;
       const uint32_t aph = (lt / C::kAcc) & 1;
-      const int grow = mt * kBM + (int)row;
-      const bool live = grow < p.M;
+      FRS_GT(10);
       mbar_wait_c(&tfull[acc], aph, 104u);
       tc_fence_after();
+      FRS_GT(11);
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN + half * C::kColsPerThread;
       uint32_t v[32];
       if (p.debug & 1) {
@@ -455,6 +505,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int ct = (int)half * C::kColsPerThread + c * 32;  // column within the tile
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
+          FRS_GT(12);
           if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained: the next tile's MMAs may overwrite it
             tc_fence_before();
             __syncwarp();
@@ -485,15 +536,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(v[2 * j]) + bs[2 * j];
-              float b = __uint_as_float(v[2 * j + 1]) + bs[2 * j + 1];
-              if constexpr (EPI == kEpiGelu) {
-                a = gelu_erf(a);
-                b = gelu_erf(b);
-              } else {
-                a *= sc;
-                b *= sc;
-              }
+              float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+              const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
+              fadd2(a, b, bb.x, bb.y);
+              if constexpr (EPI == kEpiGelu) gelu_erf2(a, b);
+              else fmul2(a, b, sc, sc);
               o[j] = pack_bf16x2(a, b);
             }
             stage_and_store(o, nt * BN + ct, mt);
@@ -502,7 +549,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       } else {
         // bias (+ the residual, which the last three K-steps added to the accumulator), row statistics of this
         // CTA's 192 columns; the pre-LayerNorm value goes back to TMEM (fp32)
-        float sum = 0.f, sq = 0.f;
+        float sum = 0.f, sq = 0.f, sum1 = 0.f, sq1 = 0.f;  // even / odd columns (packed pairs)
 #pragma unroll
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
           const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
@@ -511,16 +558,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const float* bs = sbias + col;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(v[2 * j]) + bs[2 * j];  // the residual is already in the accumulator
-            const float b = __uint_as_float(v[2 * j + 1]) + bs[2 * j + 1];
-            sum += a + b;
-            sq += a * a + b * b;
+            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+            const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
+            fadd2(a, b, bb.x, bb.y);  // the residual is already in the accumulator
+            fadd2(sum, sum1, a, b);
+            ffma2_acc(sq, sq1, a, b, a, b);
             v[2 * j] = __float_as_uint(a);
             v[2 * j + 1] = __float_as_uint(b);
           }
           tmem_st_32x32(taddr + c * 32, v);
         }
         tmem_st_wait();
+        sum += sum1;
+        sq += sq1;
         // partial statistics: slots {0,1} = this CTA's column quarters, {2,3} = the peer's (written by the
         // peer through distributed shared memory).  Double-buffered by tile parity.
         const uint32_t par = lt & 1;
@@ -555,9 +605,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * sgamma[col + 2 * j] + sbeta[col + 2 * j];
-            const float b =
-                (__uint_as_float(v[2 * j + 1]) - mean) * rstd * sgamma[col + 2 * j + 1] + sbeta[col + 2 * j + 1];
+            // ((v - mean) * rstd) * gamma + beta on the packed pipes
+            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+            const float2 gg = *reinterpret_cast<const float2*>(sgamma + col + 2 * j);
+            const float2 be = *reinterpret_cast<const float2*>(sbeta + col + 2 * j);
+            fadd2(a, b, -mean, -mean);
+            fmul2(a, b, rstd, rstd);
+            ffma2(a, b, gg.x, gg.y, be.x, be.y);
             o[j] = pack_bf16x2(a, b);
           }
           stage_and_store(o, col, mt);
@@ -1118,6 +1172,32 @@ static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUte
   GemmParams pd = p;
   static const int dbg = getenv("FRS_GEMM_DEBUG") ? atoi(getenv("FRS_GEMM_DEBUG")) : 0;
   pd.debug = dbg;
+  pd.trace = nullptr;
+#ifdef FRS_GEMM_TRACE
+  static long long* gth = nullptr;
+  static int gcalls = 0;
+  const bool dump = ++gcalls == 20;  // one warm launch of this kernel class
+  if (dump) {
+    if (!gth) cudaHostAlloc(&gth, 3 * kGTraceCap * 8, cudaHostAllocMapped);
+    memset(gth, 0, 3 * kGTraceCap * 8);
+    cudaHostGetDevicePointer(&pd.trace, gth, 0);
+  }
+  struct Dump {
+    bool on; int epi; long long* h; cudaStream_t st;
+    ~Dump() {
+      if (!on) return;
+      cudaStreamSynchronize(st);
+      char name[64];
+      snprintf(name, sizeof name, "gpurun_out/gemm_trace_%d.txt", epi);
+      FILE* f = fopen(name, "w");
+      if (!f) return;
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < kGTraceCap && h[r * kGTraceCap + i]; ++i)
+          fprintf(f, "%d %lld %lld\n", r, h[r * kGTraceCap + i] >> 8, h[r * kGTraceCap + i] & 255);
+      fclose(f);
+    }
+  } dumper{dump, EPI, gth, st};
+#endif
   if constexpr (EPI == kEpiResLN) {
     // one cluster of two CTAs per 128-row tile (column halves), persistent over the row tiles
     if (p.N != 2 * BN) return cudaErrorInvalidValue;

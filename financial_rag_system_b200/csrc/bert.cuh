@@ -41,6 +41,7 @@ struct GemmParams {
   const float* beta;
   float eps;
   int debug;  // FRS_GEMM_DEBUG (measurement aid): 1 = epilogue only drains TMEM (no math, no stores)
+  long long* trace;  // -DFRS_GEMM_TRACE builds: event timeline of CTA 0 (see launch_gemm_t), else null
 };
 
 // one entry per (sequence, 128-query block)

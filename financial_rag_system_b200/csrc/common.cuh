@@ -354,6 +354,38 @@ __device__ __forceinline__ void fadd2(float& a, float& b, float c, float d) {
       : "+f"(a), "+f"(b)
       : "f"(c), "f"(d));
 }
+// packed fp32 pairs: one FMUL2 / FFMA2 issue slot per two elements (sm_100 f32x2 arithmetic)
+__device__ __forceinline__ void fmul2(float& a, float& b, float c, float d) {
+  asm("{\n\t.reg .b64 x, y;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %3};\n\t"
+      "mul.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b)
+      : "f"(c), "f"(d));
+}
+// (a, b) = (a, b) * (c, d) + (e, f)
+__device__ __forceinline__ void ffma2(float& a, float& b, float c, float d, float e, float f) {
+  asm("{\n\t.reg .b64 x, y, z;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %3};\n\t"
+      "mov.b64 z, {%4, %5};\n\t"
+      "fma.rn.f32x2 x, x, y, z;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b)
+      : "f"(c), "f"(d), "f"(e), "f"(f));
+}
+// (acc0, acc1) += (a, b) * (c, d)
+__device__ __forceinline__ void ffma2_acc(float& acc0, float& acc1, float a, float b, float c, float d) {
+  asm("{\n\t.reg .b64 x, y, z;\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 y, {%4, %5};\n\t"
+      "mov.b64 z, {%0, %1};\n\t"
+      "fma.rn.f32x2 z, x, y, z;\n\t"
+      "mov.b64 {%0, %1}, z;\n\t}"
+      : "+f"(acc0), "+f"(acc1)
+      : "f"(a), "f"(b), "f"(c), "f"(d));
+}
 // three-input maximum (one FMNMX3 on sm_100)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
