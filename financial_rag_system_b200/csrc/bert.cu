@@ -220,7 +220,7 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ typ
 // ---------------------------------------------------------------------------------------------
 constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmEpiThreads = 32 * kGemmEpiWarps;
-constexpr int kGemmThreads = 64 + kGemmEpiThreads;
+constexpr int kGemmThreads = 64 + kGemmEpiThreads + 64;  // + one TMA-store warp per column-half group
 constexpr int kNSub = 192;  // N of one tcgen05.mma / rows of one weight TMA box
 
 template <int BN>
@@ -251,6 +251,8 @@ struct GemmCfg {
 // stored the moment it is staged, and its box is only reused three chunks later — the stores never sit
 // on the epilogue's critical path.  Named barrier 2 + group.
 constexpr int kChunkBox = kBM * 64;  // 128 rows x 32 bf16
+constexpr uint32_t kBarStaged = 2;   // named barriers: staged(group, box) = 2 + 6 group + box, free = + 3
+constexpr uint32_t kBarFree = 5;
 
 // ResLN (bias + residual + LayerNorm over the 384-wide row) runs on a CLUSTER OF TWO CTAs: each CTA owns
 // one 192-column half of the same 128-row tile — the same 2-accumulator pipeline as the other GEMMs, so
@@ -443,47 +445,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         FRS_GT(4);
       }
     }
+  } else if (warp >= 2 + kGemmEpiWarps) {
+    // ===================== TMA-store warps (one per column-half group) =====================
+    // The epilogue warps only ARRIVE on the "staged" barrier of a box and go on with the next chunk; this warp
+    // waits for it, issues the TMA store, waits until the store has read the box and arrives on its "free"
+    // barrier, which an epilogue thread checks three chunks later.  (With the store issued by an epilogue
+    // thread, every chunk paid a 128-thread barrier plus ~280 clk of TMA issue + read wait.)
+    const uint32_t g = warp - (2 + kGemmEpiWarps);
+    uint8_t* const sgroup = sout0 + g * (3 * kChunkBox);
+    if (!(p.debug & 1)) {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmap_out);
+        if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
+      }
+      int my_tiles = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) ++my_tiles;
+      const uint32_t total = 3u * (uint32_t)my_tiles;
+      uint32_t n = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
+        const bool transposed = EPI == kEpiQKV && nt * BN >= 2 * kHid;
+        for (int c = 0; c < C::kColsPerThread / 32; ++c, ++n) {
+          const uint32_t b = n % 3;
+          uint8_t* box = sgroup + b * kChunkBox;
+          const int ct = (int)g * C::kColsPerThread + c * 32;  // column within the tile
+          named_bar_sync(kBarStaged + g * 6 + b, 160);
+          if (lane == 0) {
+            if (transposed) {
+              tma_store_2d(&tmap_out2, box, mt * kBM, nt * BN - 2 * kHid + ct);
+              tma_store_2d(&tmap_out2, box + 4096, mt * kBM + 64, nt * BN - 2 * kHid + ct);
+            } else {
+              tma_store_2d(&tmap_out, box, nt * BN + ct, mt * kBM);
+            }
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          __syncwarp();
+          if (n + 3 < total) named_bar_arrive(kBarFree + g * 6 + b, 160);  // (the last three have no taker)
+        }
+      }
+      if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store
+    }
   } else {
     // ===================== epilogue =====================
     const uint32_t quarter = warp & 3;           // TMEM lanes 32*quarter .. +32 are visible to this warp
     const uint32_t half = (warp - 2) >> 2;       // which half of the tile's columns
     const uint32_t row = quarter * 32 + lane;    // row within the tile
-    const bool issuer = (threadIdx.x & 127) == 64;  // first thread of each column-half group owns its TMA stores
     uint8_t* const sgroup = sout0 + half * (3 * kChunkBox);
-    if (issuer) {
-      tma_prefetch_desc(&tmap_out);
-      if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
-    }
     uint32_t nchunk = 0;  // chunks staged so far by this group (ring position)
 #ifdef FRS_GEMM_TRACE
     long long* gtr = (p.trace && blockIdx.x == 0 && threadIdx.x == 64) ? p.trace + kGTraceCap : nullptr;
     int gtn = 0;
 #endif
-    // stage 32 columns (packed bf16 pairs o[16]) of this thread's row, then store the box [128 rows x 32 cols].
+    // box of the next chunk, free again: the store warp has seen the store of three chunks ago read it
+    auto next_box = [&]() -> uint8_t* {
+      const uint32_t b = nchunk % 3;
+      if (nchunk >= 3) named_bar_sync(kBarFree + half * 6 + b, 160);
+      return sgroup + b * kChunkBox;
+    };
+    // the chunk is in its box: hand it to the store warp and go on (no wait)
+    auto chunk_staged = [&]() {
+      FRS_GT(13);
+      fence_proxy_async();
+      named_bar_arrive(kBarStaged + half * 6 + (nchunk % 3), 160);
+      FRS_GT(14);
+      ++nchunk;
+    };
+    // stage 32 columns (packed bf16 pairs o[16]) of this thread's row as a box [128 rows x 32 cols]
     // (Staging the whole half tile and storing its three boxes behind one barrier measured 5 % SLOWER: the
     // chunk-by-chunk stores overlap the rest of the tile's epilogue.)
-    auto stage_and_store = [&](const uint32_t (&o)[16], int col, int mt) {
-      uint8_t* box = sgroup + (nchunk % 3) * kChunkBox;
-      uint8_t* dst = box + row * 64;  // SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
+    auto stage_and_store = [&](const uint32_t (&o)[16]) {
+      uint8_t* dst = next_box() + row * 64;  // SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(dst + ((j ^ ((row >> 1) & 3)) << 4)) =
             make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      FRS_GT(13);
-      fence_proxy_async();
-      named_bar_sync(2 + half, 128);
-      FRS_GT(14);
-      if (issuer) {
-        tma_store_2d(&tmap_out, box, col, mt * kBM);
-        tma_store_commit();
-        tma_store_wait_read<1>();  // the store issued one chunk ago has left shared memory
-      }
-      FRS_GT(15);
-      ++nchunk;
+      chunk_staged();
     };
     uint32_t lt = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
-      const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
+      const int nt = kPair ? (int)crank : tile % nt_count;
       const uint32_t acc = lt % C::kAcc;
       const uint32_t aph = (lt / C::kAcc) & 1;
       FRS_GT(10);
@@ -515,22 +556,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (transposed) {
             // value projection: stored transposed, vt[dim][token], so that it is the K-major B operand of
             // P.V in the attention kernel.  Two boxes [32 dims][64 tokens] (SWIZZLE_128B) per chunk.
-            uint8_t* box = sgroup + (nchunk % 3) * kChunkBox;
-            uint8_t* dst = box + (row >> 6) * 4096 + (row & 7) * 2;
+            uint8_t* dst = next_box() + (row >> 6) * 4096 + (row & 7) * 2;
             const uint32_t tchunk = (row & 63) >> 3;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               *reinterpret_cast<__nv_bfloat16*>(dst + j * 128 + ((tchunk ^ (j & 7)) << 4)) =
                   __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
-            fence_proxy_async();
-            named_bar_sync(2 + half, 128);
-            if (issuer) {
-              tma_store_2d(&tmap_out2, box, mt * kBM, nt * BN - 2 * kHid + ct);
-              tma_store_2d(&tmap_out2, box + 4096, mt * kBM + 64, nt * BN - 2 * kHid + ct);
-              tma_store_commit();
-              tma_store_wait_read<1>();
-            }
-            ++nchunk;
+            chunk_staged();
           } else {
             const float sc = (EPI == kEpiQKV && nt * BN < kHid) ? p.qscale : 1.0f;
             uint32_t o[16];
@@ -543,7 +575,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               else fmul2(a, b, sc, sc);
               o[j] = pack_bf16x2(a, b);
             }
-            stage_and_store(o, nt * BN + ct, mt);
+            stage_and_store(o);
           }
         }
       } else {
@@ -614,11 +646,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             ffma2(a, b, gg.x, gg.y, be.x, be.y);
             o[j] = pack_bf16x2(a, b);
           }
-          stage_and_store(o, col, mt);
+          stage_and_store(o);
         }
       }
     }
-    if (issuer) tma_store_wait<0>();  // shared memory must outlive the last store
   }
   tc_fence_before();
   __syncthreads();

@@ -151,6 +151,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// producer side of a named barrier: counts this thread in and does not wait
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // barrier + OR-reduction of a predicate over the participating threads
 __device__ __forceinline__ bool named_bar_or(uint32_t id, uint32_t nthreads, bool pred) {
   uint32_t r;
