@@ -274,7 +274,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const GemmParams p) {
   using C = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array keeps the pointer in the shared address space: rounding the
+  // pointer through uintptr_t made every staging access a generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = sm;
   uint8_t* sout0 = sm + C::kOut;
   float* sbias = reinterpret_cast<float*>(sm + C::kParF);
@@ -501,6 +503,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     auto next_box = [&]() -> uint8_t* {
       const uint32_t b = nchunk % 3;
       if (nchunk >= 3) named_bar_sync(kBarFree + half * 6 + b, 160);
+      FRS_GT(16);
       return sgroup + b * kChunkBox;
     };
     // the chunk is in its box: hand it to the store warp and go on (no wait)
@@ -556,12 +559,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (transposed) {
             // value projection: stored transposed, vt[dim][token], so that it is the K-major B operand of
             // P.V in the attention kernel.  Two boxes [32 dims][64 tokens] (SWIZZLE_128B) per chunk.
-            uint8_t* dst = next_box() + (row >> 6) * 4096 + (row & 7) * 2;
-            const uint32_t tchunk = (row & 63) >> 3;
+            // Two tokens (rows r, r+1 = neighbouring lanes) share a 32-bit word of a vt row: the even lane writes
+            // the even dims of the pair, the odd lane the odd dims, after one shuffle per dim pair.  (32 two-byte
+            // stores per thread took ~1700 clk per chunk: ~50 clk per STS.U16 — a third of the QKV tiles.)
+            const uint32_t odd = row & 1;
+            uint8_t* dst = next_box() + (row >> 6) * 4096 + (row & 6) * 2 + odd * 128;
+            const uint32_t tch = ((row & 63) >> 3) ^ odd;
+            // (bias first, for all 32 dims: a shared-memory load behind a staging store cannot be hoisted above
+            // it — the compiler has to assume they alias — and the loop ran fully serialised, 80 clk per dim pair)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              *reinterpret_cast<__nv_bfloat16*>(dst + j * 128 + ((tchunk ^ (j & 7)) << 4)) =
-                  __float2bfloat16_rn(__uint_as_float(v[j]) + bs[j]);
+            for (int jj = 0; jj < 16; ++jj) {
+              float e = __uint_as_float(v[2 * jj]), o = __uint_as_float(v[2 * jj + 1]);
+              const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * jj);
+              fadd2(e, o, bb.x, bb.y);
+              v[2 * jj] = __float_as_uint(e);
+              v[2 * jj + 1] = __float_as_uint(o);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const float e = __uint_as_float(v[2 * jj]), o = __uint_as_float(v[2 * jj + 1]);
+              const float got = __shfl_xor_sync(0xffffffffu, odd ? e : o, 1);
+              const uint32_t word = odd ? pack_bf16x2(got, o) : pack_bf16x2(e, got);  // low half = the lower token
+              *reinterpret_cast<uint32_t*>(dst + (2 * jj) * 128 + ((tch ^ ((2 * jj) & 7)) << 4)) = word;
+            }
             chunk_staged();
           } else {
             const float sc = (EPI == kEpiQKV && nt * BN < kHid) ? p.qscale : 1.0f;
@@ -601,6 +621,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_st_32x32(taddr + c * 32, v);
         }
         tmem_st_wait();
+        FRS_GT(17);
         sum += sum1;
         sq += sq1;
         // partial statistics: slots {0,1} = this CTA's column quarters, {2,3} = the peer's (written by the
@@ -617,6 +638,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             if (++spins > (1u << 22)) trap_with_code(120u, (lt >> 1) & 1);
           }
         }
+        FRS_GT(18);
         const float2 s0 = st[row], s1 = st[128 + row], s2 = st[256 + row], s3 = st[384 + row];
         // (local + local) + (peer + peer): the same two sums in both CTAs, so both see identical statistics
         const float tsum = (s0.x + s1.x) + (s2.x + s3.x);
@@ -702,7 +724,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
                  const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array keeps the pointer in the shared address space: rounding the
+  // pointer through uintptr_t made every staging access a generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* q_full = reinterpret_cast<uint64_t*>(sm + AttnSmem::bars);
   uint64_t* q_empty = q_full + 2;
   uint64_t* kv_full = q_empty + 2;

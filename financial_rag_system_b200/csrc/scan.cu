@@ -410,7 +410,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
   using C = ScanCfg<F32>;
   using S = ScanSmem<F32>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array keeps the pointer in the shared address space: rounding the
+  // pointer through uintptr_t made every staging access a generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = sm + S::ring;
   uint8_t* qop = sm + S::qop;
   uint64_t* keys = reinterpret_cast<uint64_t*>(sm + S::keys);
