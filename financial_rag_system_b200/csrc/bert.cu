@@ -13,7 +13,8 @@
 //
 // Every GEMM is tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM) fed by TMA into
 // SWIZZLE_128B shared-memory slabs; warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM
-// allocation), warps 2..9 epilogue / softmax (a thread owns one token row = one TMEM lane).
+// allocation; the warp runs converged and the lane elected by elect.sync issues), warps 2..9 epilogue /
+// softmax (a thread owns one token row = one TMEM lane), GEMM warps 10..11 TMA stores.
 #include <math.h>
 #include <stdlib.h>
 
@@ -686,9 +687,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // is selected by starting the MMA's K slices 64 bytes into the row.  V is read from its transposed
 // copy vt[dim][token] so that keys are the K dimension of P.V.
 // Warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}; warpgroups 1 and 2 = the softmax threads of
-// head 0 / head 1 of the pair.  A softmax thread keeps a whole 128-key score row plus its 32-wide
-// output accumulator in registers, so the register file is re-divided at kernel start
-// (setmaxnreg): 40 per thread for warpgroup 0, 232 for the softmax warpgroups.
+// head 0 / head 1 of the pair.  A softmax thread keeps a whole 128-key score row in registers, so the
+// register file is re-divided at kernel start (setmaxnreg): 64 per thread for warpgroup 0, 216 for the
+// softmax warpgroups.  P goes back to tensor memory (the A operand of P.V) and O stays there for the whole
+// item; see the softmax branch for the lazy reference maximum and the turn-taking of the two heads.
 constexpr int kAttnThreads = 384;
 constexpr int kAttnRegsLow = 64;
 constexpr int kAttnRegsHigh = 216;
