@@ -221,6 +221,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # the exchange is 15 KB per rank (latency-bound): keep NCCL inside the SMs the scan leaves free
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
@@ -271,6 +274,9 @@ def run_ours(args):
         dist.broadcast(qc, 0)
     qm = torch.full((NQ,), TICKER_MASK - (1 << 32), dtype=torch.int64).to(torch.int32).to(dev)
     sh = ShardedIndex(ix, rank, world) if world > 1 else None
+    if os.environ.get("FRS_SCAN_GRID"):  # experiment knob: CTAs of the persistent scan kernel (default: one per SM)
+        ix.set_scan_grid(int(os.environ["FRS_SCAN_GRID"]))
+    shard_sync = bool(os.environ.get("FRS_SHARD_SYNC"))  # experiment knob: exchange + final merge on the scan's stream
     tiles_dev, n_tiles_total = None, (length + 127) // 128
     if grouped:
         # the tiles that hold rows of the batch's tickers (what Collection._batch_tiles computes on the host)
@@ -287,6 +293,8 @@ def run_ours(args):
             return ix.search_tiles(q, qc, qm, K, tiles_dev)
         if sh is None:
             return ix.search(q, qc, qm, K)
+        if shard_sync:
+            return sh.search(q, qc, qm, K)
         return sh.search_async(q, qc, qm, K)
 
     def barrier():
@@ -308,7 +316,7 @@ def run_ours(args):
     last = None
     for _ in range(args.steps):
         last = step()
-    if sh is not None:
+    if sh is not None and sh._side is not None:
         torch.cuda.current_stream(dev).wait_stream(sh._side)
     e1.record()
     if rank == 0:
@@ -320,7 +328,7 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ids, scores = last.wait() if sh is not None else last
+    ids, scores = last.wait() if (sh is not None and not shard_sync) else last
     if grouped:
         assert ids[:, 0].cpu().numpy().tolist() == q_rows.tolist(), "every query is a perturbed copy of its source row"
     else:

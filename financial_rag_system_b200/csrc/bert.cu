@@ -918,7 +918,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     // The output of an item (last O + normalisation + stores) is written while the FIRST block of the next item
     // is in flight: its P.V round trip and the QBlock fetch of the next item (prefetched one item ahead) used
     // to sit between two items with the MUFU idle.
-    constexpr float kLazyLog2 = 8.0f;
+#ifndef FRS_LAZY_LOG2
+#define FRS_LAZY_LOG2 8.0f
+#endif
+    constexpr float kLazyLog2 = FRS_LAZY_LOG2;  // -DFRS_LAZY_LOG2=0.f: every increase of the maximum rescales (exercises the rare path)
     float m = -INFINITY, l = 0.f;
     QBlock qb_next = p.qblk[(blockIdx.x < n_items ? blockIdx.x : 0) / kHeadPairs];
     __nv_bfloat16* dst_prev = nullptr;  // context row of this thread in the item being accumulated (null: padding row)
