@@ -1065,6 +1065,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         // FADD2 of the row sum right behind the two MUFUs it consumes: the warp stalled ~10 clk per pair on
         // the MUFU latency and an exclusive pass took 1600 clk instead of 128 x 8.)
         constexpr int kExpLag = 6;
+#ifndef FRS_ATTN_FMA_OF4
+#define FRS_ATTN_FMA_OF4 0
+#endif
+        constexpr int kExpFmaOf4 = FRS_ATTN_FMA_OF4;
 #pragma unroll
         for (int j = 0; j < 64 + kExpLag; ++j) {
           if (j < 64) {
@@ -1072,8 +1076,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
             const int i = (j & 15) * 2;
             float a = __uint_as_float(sv[i]), b = __uint_as_float(sv[i + 1]);
             fadd2(a, b, -m, -m);  // FADD2: one issue slot per score pair
-            sv[i] = __float_as_uint(ex2_approx(a));
-            sv[i + 1] = __float_as_uint(ex2_approx(b));
+            // kExpFmaOf4 of every four score pairs can take their exponentials on the FMA pipes (exp2_pair_fma)
+            // instead of the MUFU.  Measured (-DFRS_ATTN_FMA_OF4=1..4): 1.78 / 1.84 / 2.19 / 2.57 ms per pass
+            // against 1.78 with the MUFU alone — with ~200 registers live the cubic's dependent chain does not
+            // interleave across pairs (36 clk per pair) — so the default is 0.
+            if ((j & 3) < kExpFmaOf4) {
+              exp2_pair_fma(a, b);
+            } else {
+              a = ex2_approx(a);
+              b = ex2_approx(b);
+            }
+            sv[i] = __float_as_uint(a);
+            sv[i + 1] = __float_as_uint(b);
           }
           if (j >= kExpLag) {
             const int jj = j - kExpLag;

@@ -390,6 +390,27 @@ __device__ __forceinline__ void ffma2_acc(float& acc0, float& acc1, float a, flo
       : "+f"(acc0), "+f"(acc1)
       : "f"(a), "f"(b), "f"(c), "f"(d));
 }
+// 2^a, 2^b on the FMA pipes (no MUFU): x is clamped to >= -125, split by the magic-number addition into
+// n = round(x) (low mantissa bits of r = x + 1.5 * 2^23) and f = x - n in [-0.5, 0.5], 2^f is a cubic (minimax,
+// relative error 7.5e-5 — the result is rounded to bf16 anyway) and n is added to the exponent field.
+// Per PAIR: 2 FMNMX + 3 FADD2/FFMA2 + 3 FFMA2 + 2 integer ops = 10 issue slots; two MUFU.EX2 hold their own
+// warp for 16 clk.  Valid for x <= 120.
+__device__ __forceinline__ void exp2_pair_fma(float& a, float& b) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  a = fmaxf(a, -125.0f);
+  b = fmaxf(b, -125.0f);
+  float ra = a, rb = b;
+  fadd2(ra, rb, kMagic, kMagic);
+  float na = ra, nb = rb;
+  fadd2(na, nb, -kMagic, -kMagic);
+  ffma2(na, nb, -1.0f, -1.0f, a, b);  // f = x - n
+  float pa = 0.0551716685295105f, pb = 0.0551716685295105f;
+  ffma2(pa, pb, na, nb, 0.2426111251115799f, 0.2426111251115799f);
+  ffma2(pa, pb, na, nb, 0.6932609677314758f, 0.6932609677314758f);
+  ffma2(pa, pb, na, nb, 0.9999280571937561f, 0.9999280571937561f);
+  a = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ra) << 23));
+  b = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(rb) << 23));
+}
 // three-input maximum (one FMNMX3 on sm_100)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
