@@ -224,13 +224,13 @@ constexpr int kGemmEpiThreads = 32 * kGemmEpiWarps;
 constexpr int kGemmThreads = 64 + kGemmEpiThreads + 64;  // + one TMA-store warp per column-half group
 constexpr int kNSub = 192;  // N of one tcgen05.mma / rows of one weight TMA box
 
-template <int BN>
+template <int BN, bool TWO>
 struct GemmCfg {
   static_assert(BN == 192, "tile N is 192");
   static constexpr int kStageA = kBM * 128;    // 128 rows x 64 bf16
-  static constexpr int kStageB = BN * 128;     // BN rows x 64 bf16
+  static constexpr int kStageB = (TWO ? BN / 2 : BN) * 128;  // weight rows x 64 bf16 (CTA pair: half of them per CTA)
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = TWO ? 6 : 4;  // 28 KB stages leave room for six
   static constexpr int kAcc = 2;  // TMEM accumulator stages (2 x 192 columns): epilogue(i) overlaps MMA(i+1)
   static constexpr int kNSplit = BN / kNSub;
   static constexpr int kColsPerThread = BN / 2;   // two epilogue warps share a TMEM lane quarter
@@ -240,9 +240,10 @@ struct GemmCfg {
   static constexpr int kOutBufs = 1;  // (a second buffer costs a ring stage and measured slower)
   static constexpr int kParF = kOut + kOutBufs * kOutBytes;  // fp32 params: bias[1536] | gamma[384] | beta[384]
   static constexpr int kStat = kParF + (1536 + 768) * 4;  // ResLN: float2 [2 parity][4 partials][128 rows]
-  static constexpr int kBars = kStat + 2 * 4 * 128 * 8;
+  static constexpr int kBars = kStat + (TWO ? 0 : 2 * 4 * 128 * 8);
   static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc + 2) * 8;
   static constexpr int kTotal = kHolder + 16;
+  static_assert(kTotal + 1024 <= 232448, "shared memory budget");
 };
 
 // Output path of every epilogue: registers -> swizzled staging box in shared memory -> TMA store.
@@ -264,7 +265,12 @@ constexpr uint32_t kBarFree = 5;
 // of the first epilogue warp, role 2 = TMA producer (dumped to gpurun_out/gemm_trace_<epi>.txt)
 #ifdef FRS_GEMM_TRACE
 constexpr int kGTraceCap = 4096;
-#define FRS_GT(id) do { if (gtr && gtn < kGTraceCap) gtr[gtn++] = (clock64() << 8) | (long long)(id); } while (0)
+__device__ __forceinline__ long long gt_now() {  // ns, comparable across SMs (the two CTAs of a pair)
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FRS_GT(id) do { if (gtr && gtn < kGTraceCap) gtr[gtn++] = (gt_now() << 8) | (long long)(id); } while (0)
 #else
 #define FRS_GT(id) do { } while (0)
 #endif
@@ -273,7 +279,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const GemmParams p) {
-  using C = GemmCfg<BN>;
+  constexpr bool kTwoSm = EPI != kEpiResLN;  // QKV / GELU: CTA pairs along M with cta_group::2 MMAs (below)
+  using C = GemmCfg<BN, kTwoSm>;
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the pointer in the shared address space: rounding the
   // pointer through uintptr_t made every staging access a generic LD.E / ST.E instead of LDS / STS)
@@ -293,15 +300,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
+  // QKV / GELU run on CTA PAIRS with 2-SM MMAs (cta_group::2): the pair owns two consecutive 128-row tiles of one
+  // 192-column tile, every CTA loads its own A rows and HALF of the weight slab (96 rows) into its own shared
+  // memory, and the leader CTA issues one M = 256 MMA for both.  A stage is 28 KB instead of 40 KB, so six stages
+  // are in flight instead of four: the K-step time of these GEMMs was the stage round trip (~2400 clk under
+  // load) divided by the ring depth, not the tensor pipe.
   constexpr bool kPair = EPI == kEpiResLN;  // 2-CTA cluster, one column half each
   constexpr int kResSteps = BN / 64;        // ResLN: K-steps that add the residual (see the producer)
   constexpr int kEyeOff = 2048;             // ResLN: identity tile, byte offset inside the bias area (floats 512..1023)
   const int nt_count = kPair ? 1 : p.N / BN;
   const int ksteps = p.K / 64;
-  const int num_tiles = p.num_mtiles * nt_count;
-  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
-  const int tile0 = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int tile_step = kPair ? (int)num_clusters_x() : (int)gridDim.x;
+  const int num_tiles = kPair ? p.num_mtiles : ((p.num_mtiles + 1) / 2) * nt_count;  // tiles of a cluster
+  const uint32_t crank = cluster_ctarank();
+  const int tile0 = (int)cluster_id_x();
+  const int tile_step = (int)num_clusters_x();
+  // (row tile, column tile) of this CTA for a cluster tile.  A phantom row tile (odd num_mtiles) loads zeros and
+  // its stores are clipped by the tensor map.
+  auto tile_mt = [&](int tile) { return kPair ? tile : 2 * (tile / nt_count) + (int)crank; };
+  auto tile_nt = [&](int tile) { return kPair ? (int)crank : tile % nt_count; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -310,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < C::kAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kGemmEpiWarps);
+      mbar_init(&tempty[i], kTwoSm ? 2 * kGemmEpiWarps : kGemmEpiWarps);  // pair: the leader's counts both CTAs' warps
     }
     mbar_init(&xbar[0], kGemmEpiThreads);  // one arrive per epilogue thread of the peer CTA
     mbar_init(&xbar[1], kGemmEpiThreads);
@@ -343,13 +359,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     fence_proxy_async();
   }
   if (warp == 1) {
-    tmem_alloc(holder, 512);
-    tmem_relinquish();
+    if constexpr (kTwoSm) {
+      tmem_alloc2(holder, 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(holder, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if constexpr (kPair) cluster_sync_all();  // the peer's mbarriers exist before anybody arrives on them
+  cluster_sync_all();  // the peer's mbarriers exist before anybody arrives on them
   const uint32_t tmem_base = *holder;
 
   if (warp == 0) {
@@ -358,24 +379,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
 #ifdef FRS_GEMM_TRACE
-      long long* gtr = (p.trace && blockIdx.x == 0) ? p.trace + 2 * kGTraceCap : nullptr;
+      long long* gtr = nullptr;  // (role 2 = the peer CTA's epilogue warp in this build)
       int gtn = 0;
 #endif
       uint32_t it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
+        const int mt = tile_mt(tile), nt = tile_nt(tile);
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait_c(&empty[stage], ph ^ 1, 101u);
           FRS_GT(30);
-          mbar_arrive_expect_tx(&full[stage], C::kStage);
           uint8_t* sa = ring + (size_t)stage * C::kStage;
-          tma_load_2d(sa, &tmap_a, &full[stage], ks * 64, mt * kBM, kEvictNormal);
+          if constexpr (kTwoSm) {
+            // both CTAs' boxes complete on the LEADER's barrier (its MMA thread consumes both halves)
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStage);
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            tma_load_2d_cg2(sa, &tmap_a, lead_full, ks * 64, mt * kBM, kEvictNormal);
+            tma_load_2d_cg2(sa + C::kStageA, &tmap_b, lead_full, ks * 64, nt * BN + (int)crank * (BN / 2), kEvictLast);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::kStage);
+            tma_load_2d(sa, &tmap_a, &full[stage], ks * 64, mt * kBM, kEvictNormal);
 #pragma unroll
-          for (int s = 0; s < C::kNSplit; ++s)
-            tma_load_2d(sa + C::kStageA + s * (kNSub * 128), &tmap_b, &full[stage], ks * 64,
-                        nt * BN + s * kNSub, kEvictLast);
+            for (int s = 0; s < C::kNSplit; ++s)
+              tma_load_2d(sa + C::kStageA + s * (kNSub * 128), &tmap_b, &full[stage], ks * 64,
+                          nt * BN + s * kNSub, kEvictLast);
+          }
         }
         if constexpr (kPair) {
           // the residual rides through the tensor core: three more K-steps whose A slab is the residual's
@@ -397,19 +426,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     {
       const uint32_t issue = elect_one_pred();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform: stays in a uniform register
-      constexpr uint32_t idesc = make_idesc(1u, kBM, kNSub);
+      constexpr uint32_t idesc = make_idesc(1u, kTwoSm ? 2 * kBM : kBM, kNSub);
 #ifdef FRS_GEMM_TRACE
       long long* gtr = (p.trace && blockIdx.x == 0 && issue) ? p.trace : nullptr;
       int gtn = 0;
 #endif
       uint32_t it = 0, lt = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
+      for (int tile = tile0; tile < num_tiles && (!kTwoSm || crank == 0); tile += tile_step, ++lt) {
         const uint32_t acc = lt % C::kAcc;
         const uint32_t aph = (lt / C::kAcc) & 1;
         FRS_GT(1);
-        mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
+        if constexpr (kTwoSm) {  // the peer CTA's epilogue warps arrive through the cluster: acquire at cluster scope
+          uint32_t spins = 0;
+          while (!mbar_try_wait_cluster(&tempty[acc], aph ^ 1)) {
+            if (++spins > (1u << 22)) trap_with_code(102u, aph ^ 1);
+          }
+        } else {
+          mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
+        }
         tc_fence_after();
         FRS_GT(2);
+        FRS_GT(40 + acc);
         const uint32_t d_tmem = tmem_u + acc * BN;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % C::kStages;
@@ -419,14 +456,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           FRS_GT(3);
           const uint32_t sa = smem_u32(ring + (size_t)stage * C::kStage);
           const uint64_t da = make_desc_sw128(sa);
-#pragma unroll
-          for (int s = 0; s < C::kNSplit; ++s) {
-            const uint64_t db = make_desc_sw128(sa + C::kStageA + s * (kNSub * 128));
+          if constexpr (kTwoSm) {
+            const uint64_t db = make_desc_sw128(sa + C::kStageA);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              tc_mma_f16_pred(d_tmem + s * kNSub, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
+              tc_mma2_f16_pred(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
+            tc_commit2_mc_pred(&empty[stage], (uint16_t)3, issue);  // frees the stage in both CTAs
+          } else {
+#pragma unroll
+            for (int s = 0; s < C::kNSplit; ++s) {
+              const uint64_t db = make_desc_sw128(sa + C::kStageA + s * (kNSub * 128));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma_f16_pred(d_tmem + s * kNSub, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
+            }
+            tc_commit_pred(&empty[stage], issue);
           }
-          tc_commit_pred(&empty[stage], issue);
         }
         if constexpr (kPair) {
           // acc[:, 64 r + 16 kk .. + 16) += residual columns [16 kk, +16) . I16^T  (bf16 x 1.0 accumulated in fp32: exact)
@@ -444,15 +489,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tc_commit_pred(&empty[stage], issue);
           }
         }
-        tc_commit_pred(&tfull[acc], issue);
+        if constexpr (kTwoSm) tc_commit2_mc_pred(&tfull[acc], (uint16_t)3, issue);  // both CTAs' epilogues
+        else tc_commit_pred(&tfull[acc], issue);
         FRS_GT(4);
       }
     }
   } else if (warp >= 2 + kGemmEpiWarps) {
     // ===================== TMA-store warps (one per column-half group) =====================
     // The epilogue warps only ARRIVE on the "staged" barrier of a box and go on with the next chunk; this warp
-    // waits for it, issues the TMA store, waits until the store has read the box and arrives on its "free"
-    // barrier, which an epilogue thread checks three chunks later.  (With the store issued by an epilogue
+    // waits for it, issues the TMA store and, once the store of two chunks ago has read its box, arrives on that
+    // box's "free" barrier, which an epilogue thread checks before it stages the chunk after this one.  (With the store issued by an epilogue
     // thread, every chunk paid a 128-thread barrier plus ~280 clk of TMA issue + read wait.)
     const uint32_t g = warp - (2 + kGemmEpiWarps);
     uint8_t* const sgroup = sout0 + g * (3 * kChunkBox);
@@ -466,7 +512,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t total = 3u * (uint32_t)my_tiles;
       uint32_t n = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int mt = tile / nt_count, nt = kPair ? (int)crank : tile % nt_count;
+        const int mt = tile_mt(tile), nt = tile_nt(tile);
         const bool transposed = EPI == kEpiQKV && nt * BN >= 2 * kHid;
         for (int c = 0; c < C::kColsPerThread / 32; ++c, ++n) {
           const uint32_t b = n % 3;
@@ -481,10 +527,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               tma_store_2d(&tmap_out, box, nt * BN + ct, mt * kBM);
             }
             tma_store_commit();
-            tma_store_wait_read<0>();
+            // up to three stores in flight: a store takes ~700-900 clk until it has read its box (it queues behind
+            // the ring's loads in the TMA unit), and waiting for each one made the store warp — and, three chunks
+            // later, the epilogue — the bottleneck of the kernel (box-free waits of 750 clk per chunk)
+            tma_store_wait_read<2>();
           }
           __syncwarp();
-          if (n + 3 < total) named_bar_arrive(kBarFree + g * 6 + b, 160);  // (the last three have no taker)
+          // the store of chunk n - 2 has read its box: free it for chunk n + 1 (the last three have no taker)
+          if (n >= 2 && n + 1 < total) named_bar_arrive(kBarFree + g * 6 + (n - 2) % 3, 160);
         }
       }
       if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store
@@ -497,7 +547,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint8_t* const sgroup = sout0 + half * (3 * kChunkBox);
     uint32_t nchunk = 0;  // chunks staged so far by this group (ring position)
 #ifdef FRS_GEMM_TRACE
-    long long* gtr = (p.trace && blockIdx.x == 0 && threadIdx.x == 64) ? p.trace + kGTraceCap : nullptr;
+    long long* gtr = (p.trace && blockIdx.x < 2 && threadIdx.x == 64) ? p.trace + (1 + blockIdx.x) * kGTraceCap : nullptr;
     int gtn = 0;
 #endif
     // box of the next chunk, free again: the store warp has seen the store of three chunks ago read it
@@ -526,9 +576,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       chunk_staged();
     };
+    // the accumulator stage is drained: tell the MMA thread (in a CTA pair it lives in the leader CTA)
+    auto acc_release = [&](uint64_t* bar) {
+      if constexpr (kTwoSm) {
+        if (crank == 0) mbar_arrive(bar);
+        else mbar_arrive_remote(mapa_u32(smem_u32(bar), 0));
+      } else {
+        mbar_arrive(bar);
+      }
+    };
     uint32_t lt = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
-      const int nt = kPair ? (int)crank : tile % nt_count;
+      const int nt = tile_nt(tile);
       const uint32_t acc = lt % C::kAcc;
       const uint32_t aph = (lt / C::kAcc) & 1;
       FRS_GT(10);
@@ -542,7 +601,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) acc_release(&tempty[acc]);
       } else if constexpr (EPI == kEpiQKV || EPI == kEpiGelu) {
         const bool transposed = EPI == kEpiQKV && nt * BN >= 2 * kHid;  // value projection
 #pragma unroll 1
@@ -554,7 +613,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained: the next tile's MMAs may overwrite it
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) acc_release(&tempty[acc]);
+            FRS_GT(50 + acc);
           }
           const float* bs = sbias + nt * BN + ct;
           if (transposed) {
@@ -655,7 +715,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) acc_release(&tempty[acc]);
           }
           uint32_t o[16];
 #pragma unroll
@@ -676,8 +736,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (kPair) cluster_sync_all();  // the peer may still be writing into this CTA's shared memory
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();  // the peer may still be writing into this CTA's shared memory / reading its operands
+  if (warp == 1) {
+    if constexpr (kTwoSm) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1211,7 +1274,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, __n
 // ---------------------------------------------------------------------------------------------
 size_t gemm_smem_bytes(int epi) {
   (void)epi;
-  return GemmCfg<192>::kTotal + 1024;
+  return GemmCfg<192, false>::kTotal + 1024;
 }
 size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
 
@@ -1236,7 +1299,7 @@ template <int BN, int EPI>
 static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                                  const CUtensorMap& to2, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = GemmCfg<BN>::kTotal + 1024;
+  const size_t smem = GemmCfg<BN, EPI != kEpiResLN>::kTotal + 1024;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1272,30 +1335,25 @@ static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUte
     }
   } dumper{dump, EPI, gth, st};
 #endif
-  if constexpr (EPI == kEpiResLN) {
-    // one cluster of two CTAs per 128-row tile (column halves), persistent over the row tiles
-    if (p.N != 2 * BN) return cudaErrorInvalidValue;
-    if (p.num_mtiles <= 0) return cudaSuccess;
-    const int clusters = p.num_mtiles < sm_count / 2 ? p.num_mtiles : sm_count / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI>, ta, tb, to, to2, pd);
-  }
-  const int tiles = p.num_mtiles * (p.N / BN);
-  if (tiles <= 0) return cudaSuccess;
-  const int grid = tiles < sm_count ? tiles : sm_count;
-  gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, to, to2, pd);
-  return cudaGetLastError();
+  // clusters of two CTAs, persistent over the cluster's tiles: ResLN = the column halves of one 128-row tile,
+  // QKV / GELU = two consecutive row tiles of one 192-column tile under one 2-SM MMA (see gemm_kernel)
+  if (EPI == kEpiResLN && p.N != 2 * BN) return cudaErrorInvalidValue;
+  if (p.num_mtiles <= 0) return cudaSuccess;
+  const int cluster_tiles = EPI == kEpiResLN ? p.num_mtiles : ((p.num_mtiles + 1) / 2) * (p.N / BN);
+  const int clusters = cluster_tiles < sm_count / 2 ? cluster_tiles : sm_count / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI>, ta, tb, to, to2, pd);
 }
 
 cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,

@@ -130,6 +130,20 @@ __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a,
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// arrive on a peer CTA's mbarrier WITHOUT a cluster-scope release of this thread's memory operations: for signals
+// whose payload is not generic memory (a drained TMEM accumulator, ordered by tcgen05.wait::ld + tcgen05.fence).
+// (The .release.cluster form above costs ~1 us per call: measured 1056 ns against 128 ns for a local arrive.)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+// 8-byte store into a peer CTA's shared memory that completes bytes on an mbarrier of that CTA: the data carries
+// its own completion, no release fence in the sending thread
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                   cluster_addr),
+               "f"(a), "f"(b), "r"(cluster_bar_addr)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -188,6 +202,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// CTA-pair load: the box lands in THIS CTA's shared memory, the bytes complete on an mbarrier that may live in
+// the peer (leader) CTA — bar_cluster_addr is a shared::cluster address (mapa)
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+
 // shared -> global tile store (bulk async group); the issuing thread owns the group
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -221,6 +246,20 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
+}
+// ---- CTA-pair (cta_group::2) forms: one warp of EACH CTA of the pair allocates / frees; the MMA is issued by the
+// leader CTA (rank 0) for both: M = 256 (128 rows per CTA), each CTA holds its own A rows and HALF of the B rows at
+// the same shared-memory offsets, and its own half of the accumulator at the same TMEM columns.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -410,6 +449,26 @@ __device__ __forceinline__ void exp2_pair_fma(float& a, float& b) {
   ffma2(pa, pb, na, nb, 0.9999280571937561f, 0.9999280571937561f);
   a = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ra) << 23));
   b = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(rb) << 23));
+}
+__device__ __forceinline__ void tc_mma2_f16_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+// commit of the pair's MMAs: one arrival on the mbarrier at this offset of every CTA in cta_mask
+__device__ __forceinline__ void tc_commit2_mc_pred(uint64_t* bar, uint16_t cta_mask, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask), "r"(issue)
+      : "memory");
 }
 // three-input maximum (one FMNMX3 on sm_100)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
