@@ -328,8 +328,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kTwoSm ? 2 * kGemmEpiWarps : kGemmEpiWarps);  // pair: the leader's counts both CTAs' warps
     }
-    mbar_init(&xbar[0], kGemmEpiThreads);  // one arrive per epilogue thread of the peer CTA
-    mbar_init(&xbar[1], kGemmEpiThreads);
+    mbar_init(&xbar[0], 1);  // armed once per tile with the bytes of the peer's statistics (st.async)
+    mbar_init(&xbar[1], 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
@@ -690,8 +690,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t par = lt & 1;
         float2* st = sstat + par * 512;
         st[half * 128 + row] = make_float2(sum, sq);
-        st_cluster_f32x2(mapa_u32(smem_u32(st + (2 + half) * 128 + row), crank ^ 1u), sum, sq);
-        mbar_arrive_cluster(mapa_u32(smem_u32(&xbar[par]), crank ^ 1u));
+        // st.async: the 8 bytes complete on the peer's barrier themselves (a plain remote store followed by a
+        // release.cluster arrive cost every epilogue thread ~1 us per tile)
+        st_async_f32x2(mapa_u32(smem_u32(st + (2 + half) * 128 + row), crank ^ 1u), sum, sq,
+                       mapa_u32(smem_u32(&xbar[par]), crank ^ 1u));
+        if (threadIdx.x == 64) mbar_arrive_expect_tx(&xbar[par], kGemmEpiThreads * 8);  // the peer's 256 x 8 bytes
         named_bar_sync(1, kGemmEpiThreads);
         {
           uint32_t spins = 0;
