@@ -145,6 +145,21 @@ def test_embed_matches_oracle_cls_and_mean(bge):
         assert cos.min() >= 0.999, cos.min()
 
 
+@pytest.mark.parametrize("lens", [[5], [128], [129], [100, 120, 130], [512, 512, 300], [64] * 9])
+def test_odd_and_even_row_tile_counts(bge, lens):
+    """The QKV / FFN-up GEMMs run on CTA pairs that own two consecutive 128-row tiles: with an odd number of row
+    tiles the last pair has a phantom tile (zero-filled loads, stores clipped by the tensor map); one tile, an
+    exact multiple, and one row over a tile boundary are the edges."""
+    from oracle import encoder_oracle as eo
+
+    enc, w = bge
+    ids, _, cu = _random_batch(lens, 29)
+    got = enc.embed_packed(ids, cu, 0)
+    ref = eo.embed(BGE_SMALL, w, ids, cu, "cls")
+    assert np.abs(got - ref).max() <= 1e-2
+    assert (got * ref).sum(1).min() >= 0.999
+
+
 def test_last_hidden_state_matches_oracle(bge):
     from oracle import encoder_oracle as eo
 
