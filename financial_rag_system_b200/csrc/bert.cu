@@ -224,24 +224,26 @@ constexpr int kGemmEpiThreads = 32 * kGemmEpiWarps;
 constexpr int kGemmThreads = 64 + kGemmEpiThreads + 64;  // + one TMA-store warp per column-half group
 constexpr int kNSub = 192;  // N of one tcgen05.mma / rows of one weight TMA box
 
-template <int BN, bool TWO>
+// Every GEMM runs on CTA pairs with 2-SM MMAs; a CTA holds its own 128 A rows and HALF of the weight rows of a
+// K-step.  LN = the ResLN kernels: the pair's tile is 256 rows x 384 columns (two N = 192 MMAs per K = 16), each
+// CTA holds the whole 384-wide row of its 128 rows in ONE 384-column accumulator (LayerNorm needs the full row).
+template <int BN, bool LN>
 struct GemmCfg {
   static_assert(BN == 192, "tile N is 192");
   static constexpr int kStageA = kBM * 128;    // 128 rows x 64 bf16
-  static constexpr int kStageB = (TWO ? BN / 2 : BN) * 128;  // weight rows x 64 bf16 (CTA pair: half of them per CTA)
+  static constexpr int kStageB = (LN ? BN : BN / 2) * 128;  // this CTA's weight rows x 64 bf16: 2 x 96 (LN) or 96
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = TWO ? 6 : 4;  // 28 KB stages leave room for six
-  static constexpr int kAcc = 2;  // TMEM accumulator stages (2 x 192 columns): epilogue(i) overlaps MMA(i+1)
-  static constexpr int kNSplit = BN / kNSub;
-  static constexpr int kColsPerThread = BN / 2;   // two epilogue warps share a TMEM lane quarter
+  static constexpr int kStages = LN ? 4 : 6;   // 40 KB / 28 KB stages
+  static constexpr int kAcc = LN ? 1 : 2;      // TMEM accumulator stages (LN: 384 columns, the others 2 x 192)
+  static constexpr int kTileN = LN ? 2 * BN : BN;        // columns of a CTA's tile
+  static constexpr int kColsPerThread = kTileN / 2;      // two epilogue warps share a TMEM lane quarter
   static constexpr int kRing = kStages * kStage;
   static constexpr int kOut = kRing;                   // output staging for the TMA stores
-  static constexpr int kOutBytes = kBM * kNSub * 2;    // 48 KB: 128 x 192 bf16
-  static constexpr int kOutBufs = 1;  // (a second buffer costs a ring stage and measured slower)
-  static constexpr int kParF = kOut + kOutBufs * kOutBytes;  // fp32 params: bias[1536] | gamma[384] | beta[384]
-  static constexpr int kStat = kParF + (1536 + 768) * 4;  // ResLN: float2 [2 parity][4 partials][128 rows]
-  static constexpr int kBars = kStat + (TWO ? 0 : 2 * 4 * 128 * 8);
-  static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc + 2) * 8;
+  static constexpr int kOutBytes = kBM * kNSub * 2;    // 48 KB: 2 groups x 3 boxes of 128 rows x 32 bf16
+  static constexpr int kParF = kOut + kOutBytes;       // fp32 params: bias[1536] | gamma[384] | beta[384]
+  static constexpr int kStat = kParF + (1536 + 768) * 4;  // LN: per-row partial statistics of the two column halves
+  static constexpr int kBars = kStat + (LN ? 2 * 2 * 128 * 8 : 0);  // [2 tile parities][2 halves][128 rows] float2
+  static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc) * 8;
   static constexpr int kTotal = kHolder + 16;
   static_assert(kTotal + 1024 <= 232448, "shared memory budget");
 };
@@ -256,11 +258,10 @@ constexpr int kChunkBox = kBM * 64;  // 128 rows x 32 bf16
 constexpr uint32_t kBarStaged = 2;   // named barriers: staged(group, box) = 2 + 6 group + box, free = + 3
 constexpr uint32_t kBarFree = 5;
 
-// ResLN (bias + residual + LayerNorm over the 384-wide row) runs on a CLUSTER OF TWO CTAs: each CTA owns
-// one 192-column half of the same 128-row tile — the same 2-accumulator pipeline as the other GEMMs, so
-// the epilogue overlaps the next tile's MMAs (a 384-column accumulator cannot be double-buffered in 512
-// TMEM columns).  The halves exchange their per-row (sum, sum of squares) through distributed shared
-// memory: every epilogue thread stores its partial into the peer CTA and arrives on the peer's mbarrier.
+// ResLN (bias + residual + LayerNorm over the 384-wide row): each CTA of the pair owns the WHOLE row of its 128
+// rows (one 384-column accumulator: no double buffering, the epilogue of a tile is exposed, but a K-step now carries
+// 768 clk of MMA per 40 KB stage instead of 384 and the main loop no longer waits for operands).  The residual
+// rides through the tensor core as six extra K-steps against a 16 x 16 identity.
 // -DFRS_GEMM_TRACE: event timeline (clock64 << 8 | id) of CTA 0 of one launch: role 0 = MMA issuer, role 1 = lane 0
 // of the first epilogue warp, role 2 = TMA producer (dumped to gpurun_out/gemm_trace_<epi>.txt)
 #ifdef FRS_GEMM_TRACE
@@ -279,8 +280,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const GemmParams p) {
-  constexpr bool kTwoSm = EPI != kEpiResLN;  // QKV / GELU: CTA pairs along M with cta_group::2 MMAs (below)
-  using C = GemmCfg<BN, kTwoSm>;
+  constexpr bool kLN = EPI == kEpiResLN;
+  using C = GemmCfg<BN, kLN>;
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the pointer in the shared address space: rounding the
   // pointer through uintptr_t made every staging access a generic LD.E / ST.E instead of LDS / STS)
@@ -295,29 +296,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty = full + C::kStages;
   uint64_t* tfull = empty + C::kStages;
   uint64_t* tempty = tfull + C::kAcc;
-  uint64_t* xbar = tempty + C::kAcc;  // ResLN: the peer's partial statistics of tile parity 0 / 1 have landed
   uint32_t* holder = reinterpret_cast<uint32_t*>(sm + C::kHolder);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  // QKV / GELU run on CTA PAIRS with 2-SM MMAs (cta_group::2): the pair owns two consecutive 128-row tiles of one
-  // 192-column tile, every CTA loads its own A rows and HALF of the weight slab (96 rows) into its own shared
-  // memory, and the leader CTA issues one M = 256 MMA for both.  A stage is 28 KB instead of 40 KB, so six stages
-  // are in flight instead of four: the K-step time of these GEMMs was the stage round trip (~2400 clk under
-  // load) divided by the ring depth, not the tensor pipe.
-  constexpr bool kPair = EPI == kEpiResLN;  // 2-CTA cluster, one column half each
-  constexpr int kResSteps = BN / 64;        // ResLN: K-steps that add the residual (see the producer)
-  constexpr int kEyeOff = 2048;             // ResLN: identity tile, byte offset inside the bias area (floats 512..1023)
-  const int nt_count = kPair ? 1 : p.N / BN;
+  // CTA PAIRS with 2-SM MMAs (cta_group::2, M = 256): the pair owns two consecutive 128-row tiles; every CTA loads
+  // its own A rows and HALF of the weight rows of a K-step into its own shared memory (the boxes complete on the
+  // LEADER's mbarrier), and the leader CTA issues the MMAs for both.  A QKV / GELU stage is 28 KB instead of the
+  // 40 KB of a 1-SM 128 x 192 tile (six stages in flight instead of four); a ResLN stage carries twice the MMA
+  // work per byte.  The K-step time of the 1-SM kernels was the stage round trip (~2400 clk under load) divided
+  // by the ring depth, not the tensor pipe.
+  constexpr int kResSteps = kLN ? C::kTileN / 64 : 0;  // ResLN: K-steps that add the residual
+  constexpr int kEyeOff = 2048;  // ResLN: this CTA's 8 rows of the 16 x 16 identity, byte offset inside the bias area
+  const int nt_count = kLN ? 1 : p.N / BN;
   const int ksteps = p.K / 64;
-  const int num_tiles = kPair ? p.num_mtiles : ((p.num_mtiles + 1) / 2) * nt_count;  // tiles of a cluster
+  const int num_tiles = ((p.num_mtiles + 1) / 2) * nt_count;  // tiles of a cluster
   const uint32_t crank = cluster_ctarank();
   const int tile0 = (int)cluster_id_x();
   const int tile_step = (int)num_clusters_x();
   // (row tile, column tile) of this CTA for a cluster tile.  A phantom row tile (odd num_mtiles) loads zeros and
   // its stores are clipped by the tensor map.
-  auto tile_mt = [&](int tile) { return kPair ? tile : 2 * (tile / nt_count) + (int)crank; };
-  auto tile_nt = [&](int tile) { return kPair ? (int)crank : tile % nt_count; };
+  auto tile_mt = [&](int tile) { return 2 * (tile / nt_count) + (int)crank; };
+  auto tile_nt = [&](int tile) { return tile % nt_count; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -326,46 +326,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < C::kAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kTwoSm ? 2 * kGemmEpiWarps : kGemmEpiWarps);  // pair: the leader's counts both CTAs' warps
+      mbar_init(&tempty[i], 2 * kGemmEpiWarps);  // the leader's counts the epilogue warps of both CTAs
     }
-    mbar_init(&xbar[0], 1);  // armed once per tile with the bytes of the peer's statistics (st.async)
-    mbar_init(&xbar[1], 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
-  if constexpr (EPI == kEpiResLN) {
+  if constexpr (kLN) {
     for (int i = threadIdx.x; i < kHid; i += blockDim.x) {
       sgamma[i] = p.gamma[i];
       sbeta[i] = p.beta[i];
     }
-  }
-  if constexpr (kPair) {
-    // I16: a 16 x 16 bf16 identity as a K-major SWIZZLE_128B operand tile (16 rows x 128 B, columns 0..15 used):
-    // the B operand of the residual MMAs.  It lives in the part of the bias area a 384-wide GEMM does not use.
+    // I16: the 16 x 16 bf16 identity is the B operand (N = 16) of the residual MMAs; in a 2-SM MMA every CTA holds
+    // half of the B rows, so this CTA keeps rows 8 crank .. 8 crank + 7 as one K-major SWIZZLE_128B atom (8 rows x
+    // 128 B, columns 0..15 used): row i has its 1.0 at column 8 crank + i.  It lives in the part of the bias area a
+    // 384-wide GEMM does not use.
     uint8_t* eye = sm + C::kParF + kEyeOff;
-    for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {  // 16-byte chunk (n, c): columns 8c .. 8c+7 of row n
-      const int n = i >> 3, c = i & 7;
+    for (int i = threadIdx.x; i < 8 * 8; i += blockDim.x) {  // 16-byte chunk (row i, chunk c)
+      const int r = i >> 3, c = i & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (c == (n >> 3)) {
-        const uint32_t one = 0x3F80u << (16 * (n & 1));
-        const int w = (n & 7) >> 1;
+      if (c == (int)crank) {  // column 8 crank + r sits in chunk `crank`, element r of the chunk
+        const uint32_t one = 0x3F80u << (16 * (r & 1));
+        const int w = r >> 1;
         v.x = w == 0 ? one : 0u;
         v.y = w == 1 ? one : 0u;
         v.z = w == 2 ? one : 0u;
         v.w = w == 3 ? one : 0u;
       }
-      *reinterpret_cast<uint4*>(eye + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+      *reinterpret_cast<uint4*>(eye + r * 128 + ((c ^ r) << 4)) = v;
     }
     fence_proxy_async();
   }
   if (warp == 1) {
-    if constexpr (kTwoSm) {
-      tmem_alloc2(holder, 512);
-      tmem_relinquish2();
-    } else {
-      tmem_alloc(holder, 512);
-      tmem_relinquish();
-    }
+    tmem_alloc2(holder, 512);
+    tmem_relinquish2();
   }
   tc_fence_before();
   __syncthreads();
@@ -391,58 +384,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait_c(&empty[stage], ph ^ 1, 101u);
           FRS_GT(30);
           uint8_t* sa = ring + (size_t)stage * C::kStage;
-          if constexpr (kTwoSm) {
-            // both CTAs' boxes complete on the LEADER's barrier (its MMA thread consumes both halves)
-            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStage);
-            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-            tma_load_2d_cg2(sa, &tmap_a, lead_full, ks * 64, mt * kBM, kEvictNormal);
-            tma_load_2d_cg2(sa + C::kStageA, &tmap_b, lead_full, ks * 64, nt * BN + (int)crank * (BN / 2), kEvictLast);
+          // both CTAs' boxes complete on the LEADER's barrier (its MMA thread consumes both halves)
+          if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStage);
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+          tma_load_2d_cg2(sa, &tmap_a, lead_full, ks * 64, mt * kBM, kEvictNormal);
+          if constexpr (kLN) {
+            // columns [0,192) take weight rows 96 crank .. +96 of this CTA, columns [192,384) rows 192 + 96 crank ..
+            tma_load_2d_cg2(sa + C::kStageA, &tmap_b, lead_full, ks * 64, (int)crank * (BN / 2), kEvictLast);
+            tma_load_2d_cg2(sa + C::kStageA + (BN / 2) * 128, &tmap_b, lead_full, ks * 64, BN + (int)crank * (BN / 2),
+                            kEvictLast);
           } else {
-            mbar_arrive_expect_tx(&full[stage], C::kStage);
-            tma_load_2d(sa, &tmap_a, &full[stage], ks * 64, mt * kBM, kEvictNormal);
-#pragma unroll
-            for (int s = 0; s < C::kNSplit; ++s)
-              tma_load_2d(sa + C::kStageA + s * (kNSub * 128), &tmap_b, &full[stage], ks * 64,
-                          nt * BN + s * kNSub, kEvictLast);
+            tma_load_2d_cg2(sa + C::kStageA, &tmap_b, lead_full, ks * 64, nt * BN + (int)crank * (BN / 2), kEvictLast);
           }
         }
-        if constexpr (kPair) {
-          // the residual rides through the tensor core: three more K-steps whose A slab is the residual's
-          // [128 rows x 64 columns] of this CTA's column half (tmap_out2 = the residual as an A operand)
+        if constexpr (kLN) {
+          // the residual rides through the tensor core: six more K-steps whose A slab is the residual's own
+          // [128 rows x 64 columns] box (tmap_out2 = the residual as an A operand)
           for (int r = 0; r < kResSteps; ++r, ++it) {
             const uint32_t stage = it % C::kStages;
             const uint32_t ph = (it / C::kStages) & 1;
             mbar_wait_c(&empty[stage], ph ^ 1, 101u);
-            mbar_arrive_expect_tx(&full[stage], C::kStageA);
-            tma_load_2d(ring + (size_t)stage * C::kStage, &tmap_out2, &full[stage], nt * BN + r * 64, mt * kBM, kEvictNormal);
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageA);
+            tma_load_2d_cg2(ring + (size_t)stage * C::kStage, &tmap_out2, mapa_u32(smem_u32(&full[stage]), 0), r * 64,
+                            mt * kBM, kEvictNormal);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (leader CTA) =====================
     // The whole warp runs this loop converged; the elected lane executes the tcgen05 instructions
-    // (tc_mma_f16_pred / elect.sync): descriptors stay in uniform registers and the MMAs issue back to back.
-    {
+    // (elect.sync): descriptors stay in uniform registers and the MMAs issue back to back.
+    if (crank == 0) {
       const uint32_t issue = elect_one_pred();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform: stays in a uniform register
-      constexpr uint32_t idesc = make_idesc(1u, kTwoSm ? 2 * kBM : kBM, kNSub);
+      constexpr uint32_t idesc = make_idesc(1u, 2 * kBM, kNSub);
 #ifdef FRS_GEMM_TRACE
       long long* gtr = (p.trace && blockIdx.x == 0 && issue) ? p.trace : nullptr;
       int gtn = 0;
 #endif
       uint32_t it = 0, lt = 0;
-      for (int tile = tile0; tile < num_tiles && (!kTwoSm || crank == 0); tile += tile_step, ++lt) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
         const uint32_t acc = lt % C::kAcc;
         const uint32_t aph = (lt / C::kAcc) & 1;
         FRS_GT(1);
-        if constexpr (kTwoSm) {  // the peer CTA's epilogue warps arrive through the cluster: acquire at cluster scope
+        {  // the peer CTA's epilogue warps arrive through the cluster: acquire at cluster scope
           uint32_t spins = 0;
           while (!mbar_try_wait_cluster(&tempty[acc], aph ^ 1)) {
             if (++spins > (1u << 22)) trap_with_code(102u, aph ^ 1);
           }
-        } else {
-          mbar_wait_c(&tempty[acc], aph ^ 1, 102u);
         }
         tc_fence_after();
         FRS_GT(2);
@@ -456,26 +446,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           FRS_GT(3);
           const uint32_t sa = smem_u32(ring + (size_t)stage * C::kStage);
           const uint64_t da = make_desc_sw128(sa);
-          if constexpr (kTwoSm) {
-            const uint64_t db = make_desc_sw128(sa + C::kStageA);
+          const uint64_t db = make_desc_sw128(sa + C::kStageA);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              tc_mma2_f16_pred(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
-            tc_commit2_mc_pred(&empty[stage], (uint16_t)3, issue);  // frees the stage in both CTAs
-          } else {
-#pragma unroll
-            for (int s = 0; s < C::kNSplit; ++s) {
-              const uint64_t db = make_desc_sw128(sa + C::kStageA + s * (kNSub * 128));
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                tc_mma_f16_pred(d_tmem + s * kNSub, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
+          for (int kk = 0; kk < 4; ++kk) {
+            tc_mma2_f16_pred(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
+            if constexpr (kLN) {  // second column half: the CTA's second 96-row box
+              const uint64_t db1 = make_desc_sw128(sa + C::kStageA + (BN / 2) * 128);
+              tc_mma2_f16_pred(d_tmem + BN, da + 2 * kk, db1 + 2 * kk, idesc, (uint32_t)((ks | kk) != 0), issue);
             }
-            tc_commit_pred(&empty[stage], issue);
           }
+          tc_commit2_mc_pred(&empty[stage], (uint16_t)3, issue);  // frees the stage in both CTAs
         }
-        if constexpr (kPair) {
+        if constexpr (kLN) {
           // acc[:, 64 r + 16 kk .. + 16) += residual columns [16 kk, +16) . I16^T  (bf16 x 1.0 accumulated in fp32: exact)
-          constexpr uint32_t idesc_eye = make_idesc(1u, kBM, 16);
+          constexpr uint32_t idesc_eye = make_idesc(1u, 2 * kBM, 16);
           const uint64_t deye = make_desc_sw128(smem_u32(sm + C::kParF + kEyeOff));
           for (int r = 0; r < kResSteps; ++r, ++it) {
             const uint32_t stage = it % C::kStages;
@@ -485,12 +469,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint64_t da = make_desc_sw128(smem_u32(ring + (size_t)stage * C::kStage));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              tc_mma_f16_pred(d_tmem + r * 64 + kk * 16, da + 2 * kk, deye, idesc_eye, 1u, issue);
-            tc_commit_pred(&empty[stage], issue);
+              tc_mma2_f16_pred(d_tmem + r * 64 + kk * 16, da + 2 * kk, deye, idesc_eye, 1u, issue);
+            tc_commit2_mc_pred(&empty[stage], (uint16_t)3, issue);
           }
         }
-        if constexpr (kTwoSm) tc_commit2_mc_pred(&tfull[acc], (uint16_t)3, issue);  // both CTAs' epilogues
-        else tc_commit_pred(&tfull[acc], issue);
+        tc_commit2_mc_pred(&tfull[acc], (uint16_t)3, issue);  // both CTAs' epilogues
         FRS_GT(4);
       }
     }
@@ -498,8 +481,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================== TMA-store warps (one per column-half group) =====================
     // The epilogue warps only ARRIVE on the "staged" barrier of a box and go on with the next chunk; this warp
     // waits for it, issues the TMA store and, once the store of two chunks ago has read its box, arrives on that
-    // box's "free" barrier, which an epilogue thread checks before it stages the chunk after this one.  (With the store issued by an epilogue
-    // thread, every chunk paid a 128-thread barrier plus ~280 clk of TMA issue + read wait.)
+    // box's "free" barrier, which an epilogue thread checks before it stages the chunk after this one.
+    // (With the store issued by an epilogue thread, every chunk paid a 128-thread barrier plus ~280 clk of TMA
+    // issue + read wait.)
     const uint32_t g = warp - (2 + kGemmEpiWarps);
     uint8_t* const sgroup = sout0 + g * (3 * kChunkBox);
     if (!(p.debug & 1)) {
@@ -507,17 +491,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tma_prefetch_desc(&tmap_out);
         if constexpr (EPI == kEpiQKV) tma_prefetch_desc(&tmap_out2);
       }
+      constexpr uint32_t kChunks = C::kColsPerThread / 32;  // chunks of a group per tile
       int my_tiles = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) ++my_tiles;
-      const uint32_t total = 3u * (uint32_t)my_tiles;
+      const uint32_t total = kChunks * (uint32_t)my_tiles;
       uint32_t n = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int mt = tile_mt(tile), nt = tile_nt(tile);
         const bool transposed = EPI == kEpiQKV && nt * BN >= 2 * kHid;
-        for (int c = 0; c < C::kColsPerThread / 32; ++c, ++n) {
+        for (uint32_t c = 0; c < kChunks; ++c, ++n) {
           const uint32_t b = n % 3;
           uint8_t* box = sgroup + b * kChunkBox;
-          const int ct = (int)g * C::kColsPerThread + c * 32;  // column within the tile
+          const int ct = (int)g * C::kColsPerThread + (int)c * 32;  // column within the tile
           named_bar_sync(kBarStaged + g * 6 + b, 160);
           if (lane == 0) {
             if (transposed) {
@@ -576,14 +561,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       chunk_staged();
     };
-    // the accumulator stage is drained: tell the MMA thread (in a CTA pair it lives in the leader CTA)
+    // the accumulator stage is drained: tell the MMA thread, which lives in the leader CTA.  The peer arrives
+    // WITHOUT a cluster-scope release (~1 us per call): the payload is a drained TMEM accumulator, ordered by
+    // tcgen05.wait::ld + tcgen05.fence.
     auto acc_release = [&](uint64_t* bar) {
-      if constexpr (kTwoSm) {
-        if (crank == 0) mbar_arrive(bar);
-        else mbar_arrive_remote(mapa_u32(smem_u32(bar), 0));
-      } else {
-        mbar_arrive(bar);
-      }
+      if (crank == 0) mbar_arrive(bar);
+      else mbar_arrive_remote(mapa_u32(smem_u32(bar), 0));
     };
     uint32_t lt = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++lt) {
@@ -660,12 +643,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       } else {
-        // bias (+ the residual, which the last three K-steps added to the accumulator), row statistics of this
-        // CTA's 192 columns; the pre-LayerNorm value goes back to TMEM (fp32)
+        // LayerNorm over the 384-wide row: this thread owns 192 columns of its row, the thread of the other
+        // column-half group (same lane quarter) the other 192.  Pass 1: bias (the residual is already in the
+        // accumulator), row statistics, pre-LayerNorm value back to TMEM (fp32).
         float sum = 0.f, sq = 0.f, sum1 = 0.f, sq1 = 0.f;  // even / odd columns (packed pairs)
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
-          const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
+          const int col = (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           const float* bs = sbias + col;
@@ -673,7 +657,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) {
             float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
             const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
-            fadd2(a, b, bb.x, bb.y);  // the residual is already in the accumulator
+            fadd2(a, b, bb.x, bb.y);
             fadd2(sum, sum1, a, b);
             ffma2_acc(sq, sq1, a, b, a, b);
             v[2 * j] = __float_as_uint(a);
@@ -685,34 +669,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         FRS_GT(17);
         sum += sum1;
         sq += sq1;
-        // partial statistics: slots {0,1} = this CTA's column quarters, {2,3} = the peer's (written by the
-        // peer through distributed shared memory).  Double-buffered by tile parity.
-        const uint32_t par = lt & 1;
-        float2* st = sstat + par * 512;
+        // the two column halves of a row meet in shared memory (double-buffered by tile parity: a fast group may
+        // be one tile ahead of the other group's read)
+        float2* st = sstat + (lt & 1) * 256;
         st[half * 128 + row] = make_float2(sum, sq);
-        // st.async: the 8 bytes complete on the peer's barrier themselves (a plain remote store followed by a
-        // release.cluster arrive cost every epilogue thread ~1 us per tile)
-        st_async_f32x2(mapa_u32(smem_u32(st + (2 + half) * 128 + row), crank ^ 1u), sum, sq,
-                       mapa_u32(smem_u32(&xbar[par]), crank ^ 1u));
-        if (threadIdx.x == 64) mbar_arrive_expect_tx(&xbar[par], kGemmEpiThreads * 8);  // the peer's 256 x 8 bytes
         named_bar_sync(1, kGemmEpiThreads);
-        {
-          uint32_t spins = 0;
-          while (!mbar_try_wait_cluster(&xbar[par], (lt >> 1) & 1)) {
-            if (++spins > (1u << 22)) trap_with_code(120u, (lt >> 1) & 1);
-          }
-        }
         FRS_GT(18);
-        const float2 s0 = st[row], s1 = st[128 + row], s2 = st[256 + row], s3 = st[384 + row];
-        // (local + local) + (peer + peer): the same two sums in both CTAs, so both see identical statistics
-        const float tsum = (s0.x + s1.x) + (s2.x + s3.x);
-        const float tsq = (s0.y + s1.y) + (s2.y + s3.y);
+        const float2 s0 = st[row], s1 = st[128 + row];
+        const float tsum = s0.x + s1.x;  // the same two operands in the same order in both groups
+        const float tsq = s0.y + s1.y;
         const float mean = tsum * (1.0f / kHid);
         const float var = fmaxf(tsq * (1.0f / kHid) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
-          const int col = nt * BN + (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
+          const int col = (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           if (c == C::kColsPerThread / 32 - 1) {  // accumulator drained
@@ -739,11 +710,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // the peer may still be writing into this CTA's shared memory / reading its operands
-  if (warp == 1) {
-    if constexpr (kTwoSm) tmem_dealloc2(tmem_base, 512);
-    else tmem_dealloc(tmem_base, 512);
-  }
+  cluster_sync_all();  // the peer may still be reading this CTA's operands / arriving on its barriers
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1277,7 +1245,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, __n
 // ---------------------------------------------------------------------------------------------
 size_t gemm_smem_bytes(int epi) {
   (void)epi;
-  return GemmCfg<192, false>::kTotal + 1024;
+  return GemmCfg<192, false>::kTotal + 1024;  // (both configurations are within 1 KB of each other)
 }
 size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
 
@@ -1302,7 +1270,7 @@ template <int BN, int EPI>
 static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                                  const CUtensorMap& to2, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = GemmCfg<BN, EPI != kEpiResLN>::kTotal + 1024;
+  const size_t smem = GemmCfg<BN, EPI == kEpiResLN>::kTotal + 1024;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1342,7 +1310,7 @@ static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUte
   // QKV / GELU = two consecutive row tiles of one 192-column tile under one 2-SM MMA (see gemm_kernel)
   if (EPI == kEpiResLN && p.N != 2 * BN) return cudaErrorInvalidValue;
   if (p.num_mtiles <= 0) return cudaSuccess;
-  const int cluster_tiles = EPI == kEpiResLN ? p.num_mtiles : ((p.num_mtiles + 1) / 2) * (p.N / BN);
+  const int cluster_tiles = ((p.num_mtiles + 1) / 2) * (EPI == kEpiResLN ? 1 : p.N / BN);
   const int clusters = cluster_tiles < sm_count / 2 ? cluster_tiles : sm_count / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);

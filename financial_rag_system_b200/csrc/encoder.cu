@@ -227,9 +227,9 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
     EN_TRY(upload_f32(e, &L.ln2g, lw[14], kHid, dev));
     EN_TRY(upload_f32(e, &L.ln2b, lw[15], kHid, dev));
     EN_RC(abi_make_tmap_bf16(&L.t_wqkv, L.wqkv, kQkvN, kHid, 64, 96));  // CTA pair: half a weight slab per CTA
-    EN_RC(abi_make_tmap_bf16(&L.t_wo, L.wo, kHid, kHid, 64, 192));
+    EN_RC(abi_make_tmap_bf16(&L.t_wo, L.wo, kHid, kHid, 64, 96));
     EN_RC(abi_make_tmap_bf16(&L.t_w1, L.w1, kFfn, kHid, 64, 96));
-    EN_RC(abi_make_tmap_bf16(&L.t_w2, L.w2, kHid, kFfn, 64, 192));
+    EN_RC(abi_make_tmap_bf16(&L.t_w2, L.w2, kHid, kFfn, 64, 96));
   }
   if (cfg->has_head) {
     const float* const* hw = w + 5 + 16 * cfg->layers;
