@@ -137,6 +137,28 @@ __device__ __forceinline__ void gelu_erf2(float& a, float& b) {
   b = ub;
 #endif
 }
+// GELU without the MUFU: z = sat(x / 8 + 1/2) - 1/2 clamps x to [-4, 4] in one FFMA.SAT, Phi(x) - 1/2 = z Q(z^2)
+// with a degree-6 Q fitted to the erf form (scripts/fit_gelu.py --poly; max |error| of x Phi 1.9e-4 in fp32
+// evaluation over the whole real line, against <= |x| 2.7e-4 for the tanh form).  12 issue slots per PAIR on the FMA
+// pipes.  -DFRS_GELU_MIX alternates the two forms by column pair (with tanh alone the two epilogue warps of a
+// sub-partition queue on the MUFU: 260 ns of a 448 ns chunk); it measured slower and is off by default.
+__device__ __forceinline__ void gelu_poly2(float& a, float& b) {
+  float za, zb;
+  asm("fma.rn.sat.f32 %0, %1, 0f3E000000, 0f3F000000;" : "=f"(za) : "f"(a));  // sat(x * 0.125 + 0.5)
+  asm("fma.rn.sat.f32 %0, %1, 0f3E000000, 0f3F000000;" : "=f"(zb) : "f"(b));
+  fadd2(za, zb, -0.5f, -0.5f);
+  float ua = za, ub = zb;
+  fmul2(ua, ub, za, zb);  // z^2
+  float qa = 12524.2783203125f, qb = 12524.2783203125f;
+  ffma2(qa, qb, ua, ub, -13731.9296875f, -13731.9296875f);
+  ffma2(qa, qb, ua, ub, 6436.49365234375f, 6436.49365234375f);
+  ffma2(qa, qb, ua, ub, -1707.1162109375f, -1707.1162109375f);
+  ffma2(qa, qb, ua, ub, 287.4537658691406f, 287.4537658691406f);
+  ffma2(qa, qb, ua, ub, -33.061439514160156f, -33.061439514160156f);
+  ffma2(qa, qb, ua, ub, 3.1830668449401855f, 3.1830668449401855f);
+  ffma2(qa, qb, za, zb, 0.5f, 0.5f);  // Phi = z Q + 1/2
+  fmul2(a, b, qa, qb);                // x Phi
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -635,8 +657,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
               const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
               fadd2(a, b, bb.x, bb.y);
-              if constexpr (EPI == kEpiGelu) gelu_erf2(a, b);
-              else fmul2(a, b, sc, sc);
+              if constexpr (EPI == kEpiGelu) {
+#if defined(FRS_GELU_MIX) && !defined(FRS_EXACT_GELU)
+                // odd column pairs on the FMA pipes (gelu_poly2), even ones on the MUFU.  Measured: FFN-up 0.94 ms
+                // per pass against 0.84 ms with the tanh form alone (the degree-6 chain does not interleave well
+                // across pairs), so this is off by default.
+                if (j & 1) gelu_poly2(a, b);
+                else gelu_erf2(a, b);
+#else
+                gelu_erf2(a, b);
+#endif
+              } else {
+                fmul2(a, b, sc, sc);
+              }
               o[j] = pack_bf16x2(a, b);
             }
             stage_and_store(o);
