@@ -154,7 +154,7 @@ def cpu_sample_data(n_rows=CPU_SAMPLE_ROWS, seed=1234):
 
 
 def cpu_baseline(steps=2, warmup=1):
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_threads()
     rows, codes, queries, qt = cpu_sample_data()
     t = cpu_step_time(rows, codes, queries, qt, steps, warmup)
     scale = TOTAL_ROWS / CPU_SAMPLE_ROWS
@@ -166,11 +166,23 @@ def cpu_baseline(steps=2, warmup=1):
     }
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)  # OpenBLAS / OpenMP pools behind numpy (kept for the process lifetime)
+    except Exception:
+        pass
+    return cores
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_threads()
     t0 = time.perf_counter()
     # size the per-step sample so that the whole run (W + K steps) stays within ~2.5 minutes
     rows, codes, queries, qt = cpu_sample_data(50_000)
