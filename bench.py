@@ -215,7 +215,9 @@ def workload_config(n_gpus):
         "rows_total": TOTAL_ROWS, "rows_per_gpu": TOTAL_ROWS // n_gpus, "dim": DIM, "batch": NQ, "k": K,
         "filter": f"ticker == T, T ~ Zipf(1.1) over {N_TICKERS} tickers (reference main.py:218-223)",
         "corpus": "1024 unit centroids + noise of norm 0.3, L2-normalised, generated on device (seed 7)",
-        "parallelism": f"rows sharded over {n_gpus} GPU(s), one NCCL all-gather of 32x15 (score,id) per batch" if n_gpus > 1 else "1 GPU",
+        "parallelism": (f"rows sharded over {n_gpus} GPU(s); exchange of the 32x15 (score,id) lists per batch: "
+                        + ("NCCL all-gather" if os.environ.get("FRS_EXCHANGE", "p2p").lower() == "nccl"
+                           else "stores into the peers' buffers over NVLink peer memory + flags (csrc/exchange.cu)")) if n_gpus > 1 else "1 GPU",
         "l2": "inputs larger than L2 (7.7 GB corpus per step vs 126 MB L2)",
     }
 
@@ -299,6 +301,13 @@ def run_ours(args):
         full_ids, _ = ix.search(q, qc, qm, K)
         seg_ids, _ = ix.search_tiles(q, qc, qm, K, tiles_dev)
         assert torch.equal(full_ids, seg_ids), "restricted scan must return the ids of the full scan"
+
+    if sh is not None and sh.exchange == "p2p":
+        # the peer-memory exchange must return exactly what the NCCL all-gather form returns
+        ref = ShardedIndex(ix, rank, world, exchange="nccl")
+        pi, ps = sh.search(q, qc, qm, K)
+        ni, ns = ref.search(q, qc, qm, K)
+        assert torch.equal(pi, ni) and torch.equal(ps, ns), "peer-memory exchange differs from the all-gather exchange"
 
     def step():
         if tiles_dev is not None:

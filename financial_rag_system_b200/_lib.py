@@ -56,6 +56,13 @@ PROTOTYPES = {
     "frs_index_search_local": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "frs_merge_shards": (_int, [_int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
     "frs_merge_shards_packed": (_int, [_int, _vp, _int, _int, _int, _vp, _vp, _vp]),
+    "frs_exchange_create": (_int, [_int, _int, _int, _int, _int, C.POINTER(_vp)]),
+    "frs_exchange_destroy": (_int, [_vp]),
+    "frs_exchange_handle": (_int, [_vp, _vp]),
+    "frs_exchange_connect": (_int, [_vp, _vp]),
+    "frs_exchange_connect_local": (_int, [_vp, _vp]),
+    "frs_exchange_push": (_int, [_vp, _vp, _vp]),
+    "frs_exchange_wait_merge": (_int, [_vp, _vp, _vp, _vp]),
     "frs_index_last_queries": (_int, [_vp, _vp, _vp]),
     "frs_index_debug_scores": (_int, [_vp, _vp, _int, _vp, _vp]),
     "frs_index_last_stats": (_int, [_vp, C.POINTER(_i64)]),

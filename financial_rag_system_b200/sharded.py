@@ -6,7 +6,9 @@ is balanced.  A search is
 
     local pass    every rank scans its shard for all queries -> exact local top-k as
                   (float64 score, int64 global id)                       [CUDA: prep/scan/merge]
-    exchange      ONE all-gather of world * nq * k * 16 bytes (46 KB at 8 x 32 x 15)   [NCCL]
+    exchange      every rank WRITES its nq * k * 16 bytes into every peer's gather buffer over NVLink
+                  peer memory and publishes a sequence flag (csrc/exchange.cu, `PeerExchange`); or, with
+                  exchange="nccl", ONE all-gather of world * nq * k * 16 bytes           [CUDA | NCCL]
     final merge   [world, nq, k] -> [nq, k] by (score desc, id asc) on every rank      [CUDA]
 
 The per-shard lists are exact, so the result is identical to a single-shard search of the whole
@@ -44,10 +46,65 @@ class PendingSearch:
         return self.ids, self.scores
 
 
+class PeerExchange:
+    """The exchange step over NVLink peer memory (include/frs_b200.h frs_exchange_*): push = this rank's
+    [2, nq, k] block into every peer's gather buffer + a sequence flag; wait_merge = wait for all ranks' flags,
+    then the cross-shard merge.  One object per (nq, k).  Every rank calls push / wait_merge once per batch."""
+
+    def __init__(self, device: torch.device, world: int, rank: int, nq: int, k: int, group=None, connect: bool = True):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib, self._C = _lib, C
+        self.device, self.world, self.rank, self.nq, self.k = device, int(world), int(rank), int(nq), int(k)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().frs_exchange_create(device.index or 0, self.world, self.rank, self.nq, self.k, C.byref(h)))
+        self._h = h
+        if connect:
+            buf = (C.c_uint8 * 128)()
+            _lib.check(_lib.lib().frs_exchange_handle(self._h, buf))
+            mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+            every = torch.empty(self.world * 128, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            raw = bytes(every.cpu().numpy().tobytes())
+            _lib.check(_lib.lib().frs_exchange_connect(self._h, C.cast(C.c_char_p(raw), C.c_void_p)))
+
+    @staticmethod
+    def link(exchanges) -> None:
+        """In-process form: several shards of one process (tests); exchanges[r] is rank r."""
+        import ctypes as C
+
+        from . import _lib
+
+        arr = (C.c_void_p * len(exchanges))(*[e._h for e in exchanges])
+        for e in exchanges:
+            _lib.check(_lib.lib().frs_exchange_connect_local(e._h, arr))
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def push(self, local_packed: torch.Tensor) -> None:
+        assert local_packed.dtype == torch.int64 and tuple(local_packed.shape) == (2, self.nq, self.k) and local_packed.is_contiguous()
+        self._lib.check(self._lib.lib().frs_exchange_push(self._h, self._C.c_void_p(local_packed.data_ptr()), self._stream()))
+
+    def wait_merge(self):
+        out_s = torch.empty((self.nq, self.k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((self.nq, self.k), dtype=torch.int64, device=self.device)
+        self._lib.check(self._lib.lib().frs_exchange_wait_merge(self._h, self._C.c_void_p(out_s.data_ptr()),
+                                                                self._C.c_void_p(out_i.data_ptr()), self._stream()))
+        return out_i, out_s
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._lib.lib().frs_exchange_destroy(self._h)
+            self._h = None
+
+
 class ShardedIndex:
     def __init__(self, local_index, rank: int, world: int, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 device: Optional[torch.device] = None, reserve_sms: int = 8):
+                 device: Optional[torch.device] = None, reserve_sms: int = 8, exchange: Optional[str] = None):
         """local_index: a VectorIndex whose base is this shard's first global row (or any object
         when local_search/merge are injected).
 
@@ -65,6 +122,17 @@ class ShardedIndex:
         self._slot = 0
         self._slot_free = [None, None]  # event: the side stream is done with this slot's buffers
         self._bufs = {}
+        # exchange step: "p2p" = writes into the peers' buffers over NVLink (PeerExchange), "nccl" = one all-gather.
+        # The injectable CPU path (gloo tests) and world 1 use the collective form.
+        import os
+
+        cuda_path = self.world > 1 and merge is None and self.device.type == "cuda"
+        self.exchange = (exchange or os.environ.get("FRS_EXCHANGE") or ("p2p" if cuda_path else "nccl")).lower()
+        if self.exchange not in ("p2p", "nccl"):
+            raise ValueError(f"exchange must be 'p2p' or 'nccl', got {self.exchange!r}")
+        if not cuda_path:
+            self.exchange = "nccl"
+        self._peer = {}
         if self.world > 1 and local_search is None and self.device.type == "cuda" and reserve_sms > 0:
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             if sms > 2 * reserve_sms and hasattr(local_index, "set_scan_grid"):
@@ -92,6 +160,13 @@ class ShardedIndex:
         return self._bufs[key]
 
     def _exchange_and_merge(self, loc: torch.Tensor, gat: torch.Tensor, k: int):
+        if self.exchange == "p2p":
+            key = (loc.shape[1], k)
+            if key not in self._peer:  # collective on first use: every rank creates and connects it
+                self._peer[key] = PeerExchange(self.device, self.world, self.rank, loc.shape[1], k, group=self.group)
+            ex = self._peer[key]
+            ex.push(loc)
+            return ex.wait_merge()
         if self.world > 1:
             # output viewed as the concatenation of the per-rank inputs along dim 0 (what gloo expects;
             # NCCL accepts both forms)

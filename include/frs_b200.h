@@ -69,6 +69,7 @@ extern "C" {
 
 typedef struct frs_index frs_index;
 typedef struct frs_encoder frs_encoder;
+typedef struct frs_exchange frs_exchange;
 
 /* ---- library ---------------------------------------------------------- */
 int frs_version(void);
@@ -153,6 +154,22 @@ int frs_merge_shards(int device, const double* dev_scores64, const int64_t* dev_
  * plane 1 = int64 ids) so that one all-gather moves both halves of the candidates */
 int frs_merge_shards_packed(int device, const int64_t* dev_packed, int n_shards, int nq, int k,
                             float* dev_out_scores, int64_t* dev_out_ids, void* stream);
+
+/* Cross-shard exchange over NVLink peer memory (replaces the all-gather of the sharded search; the reference
+ * has one Qdrant server and no counterpart, main.py:215-239).  Every rank creates an exchange, the 128-byte
+ * handles (two CUDA IPC handles) are all-gathered by the host, frs_exchange_connect maps the peers' buffers.
+ * Per batch: frs_exchange_push writes this rank's [2][nq][k] block (as left by frs_index_search_local, nq/k as
+ * created) into every peer's gather buffer and publishes a sequence number; frs_exchange_wait_merge waits for
+ * all ranks' pushes of that sequence number and merges to the global top-k.  Both are asynchronous on `stream`;
+ * every rank must call them once per batch, in the same order.  frs_exchange_connect_local links several
+ * exchanges of ONE process by pointer (several shards on one GPU, tests). */
+int frs_exchange_create(int device, int world, int rank, int nq_max, int k_max, frs_exchange** out);
+int frs_exchange_destroy(frs_exchange* ex);
+int frs_exchange_handle(frs_exchange* ex, uint8_t* out128);
+int frs_exchange_connect(frs_exchange* ex, const uint8_t* handles_world_by_128);
+int frs_exchange_connect_local(frs_exchange* ex, frs_exchange* const* peers);
+int frs_exchange_push(frs_exchange* ex, const int64_t* dev_local_packed, void* stream);
+int frs_exchange_wait_merge(frs_exchange* ex, float* dev_out_scores, int64_t* dev_out_ids, void* stream);
 
 /* the prepared (normalised, storage-dtype-rounded) queries of the last search,
  * widened to fp32: what the scores are dot products with.  [FRS_MAX_BATCH, 384] */

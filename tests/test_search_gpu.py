@@ -264,6 +264,44 @@ def test_two_shards_on_one_gpu_equal_one_index():
         ix.close()
 
 
+def test_peer_memory_exchange_equals_one_index():
+    """The exchange step over peer memory (frs_exchange_*): three shards of ONE process linked by pointer, each
+    pushes its block into every shard's gather buffer; every shard's merge equals the single-index search.
+    Several batches in a row exercise the double-buffered slots and the monotonic sequence flags."""
+    from financial_rag_system_b200.sharded import PeerExchange
+
+    n, cuts, k, nq = 30_001, [0, 9_000, 21_345, 30_001], 15, 32
+    x, codes, g = _data(n, 37)
+    whole = _index(n, "bf16")
+    whole.add(x, codes)
+    shards = []
+    for r in range(3):
+        ix = _index(cuts[r + 1] - cuts[r], "bf16", base=cuts[r])
+        ix.add(x[cuts[r]:cuts[r + 1]], codes[cuts[r]:cuts[r + 1]])
+        shards.append(ix)
+    dev = torch.device("cuda", 0)
+    exs = [PeerExchange(dev, 3, r, nq, k, connect=False) for r in range(3)]
+    PeerExchange.link(exs)
+    for batch in range(5):
+        q = x[batch * 32:batch * 32 + nq] + 0.1 * torch.randn((nq, 384), generator=g, device="cuda")
+        qc = _i32((codes[batch * 32:batch * 32 + nq] & 0x7FFFFFFF).cpu().numpy())
+        qm = _i32(np.full(nq, TICKER, np.uint32))
+        for r in range(3):  # all pushes first: the waits of one process would otherwise wait for each other
+            loc = torch.empty((2, nq, k), dtype=torch.int64, device="cuda")
+            shards[r].search_local(q, qc, qm, k, loc[0].view(torch.float64), loc[1])
+            exs[r].push(loc)
+        wi, ws = whole.search(q, qc, qm, k)
+        for r in range(3):
+            mi, ms = exs[r].wait_merge()
+            torch.cuda.synchronize()
+            assert torch.equal(mi, wi), (batch, r)
+            assert torch.equal(ms, ws), (batch, r)
+    for e in exs:
+        e.close()
+    for ix in [whole] + shards:
+        ix.close()
+
+
 def test_concurrent_callers_on_one_index():
     """The reference calls the search from up to 25 threads (main2.py:52-53, 228)."""
     n = 20_000
