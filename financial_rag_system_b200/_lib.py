@@ -63,6 +63,7 @@ PROTOTYPES = {
     "frs_exchange_connect_local": (_int, [_vp, _vp]),
     "frs_exchange_push": (_int, [_vp, _vp, _vp]),
     "frs_exchange_wait_merge": (_int, [_vp, _vp, _vp, _vp]),
+    "frs_index_search_push": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "frs_index_last_queries": (_int, [_vp, _vp, _vp]),
     "frs_index_debug_scores": (_int, [_vp, _vp, _int, _vp, _vp]),
     "frs_index_last_stats": (_int, [_vp, C.POINTER(_i64)]),

@@ -5,7 +5,9 @@
 //
 //   push   every rank WRITES that block into slot `rank` of EVERY peer's gather buffer with plain stores through
 //          peer-mapped pointers (CUDA IPC handles opened once), fences at system scope and then publishes its
-//          sequence number in the peer's flag word;
+//          sequence number in the peer's flag word.  frs_index_search_push (index.cu) does this in the TAIL OF
+//          THE LOCAL MERGE KERNEL (scan.cu merge_kernel: one CTA per query pushes its k results, the last CTA
+//          publishes the flags); frs_exchange_push is the stand-alone form for a block that already exists;
 //   wait   a one-warp kernel spins (bounded) until all `world` flags have reached the current sequence number;
 //   merge  the existing cross-shard merge kernel runs over the local gather buffer.
 //
@@ -28,6 +30,7 @@
 #include <vector>
 
 #include "../../include/frs_b200.h"
+#include "exchange.cuh"
 #include "scan.cuh"
 
 namespace frs {
@@ -41,18 +44,6 @@ using frs::abi_set_err;
     if (_e != cudaSuccess)                                                                                        \
       return abi_set_err(FRS_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
-
-struct frs_exchange {
-  int device = 0, world = 1, rank = 0, nq_max = 0, k_max = 0;
-  size_t block_words = 0;             // 2 * nq_max * k_max 64-bit words per (slot, source rank)
-  uint64_t* gather = nullptr;         // [2 slots][world][block_words]   (local, written by the peers)
-  uint32_t* flags = nullptr;          // [world]: last sequence number pushed by each rank (local, written by peers)
-  uint64_t** d_peer_gather = nullptr; // device array [world]: every rank's gather buffer as seen from this GPU
-  uint32_t** d_peer_flags = nullptr;  // device array [world]
-  std::vector<void*> opened;          // IPC mappings to close
-  uint32_t seq = 0;
-  bool connected = false;
-};
 
 namespace {
 
@@ -102,12 +93,14 @@ extern "C" int frs_exchange_create(int device, int world, int rank, int nq_max, 
   // plain cudaMalloc (not a caching-allocator sub-block): the IPC handle names exactly this allocation
   if (cudaMalloc(&ex->gather, gbytes) != cudaSuccess || cudaMalloc(&ex->flags, (size_t)world * 4) != cudaSuccess ||
       cudaMalloc(&ex->d_peer_gather, (size_t)world * sizeof(void*)) != cudaSuccess ||
-      cudaMalloc(&ex->d_peer_flags, (size_t)world * sizeof(void*)) != cudaSuccess) {
+      cudaMalloc(&ex->d_peer_flags, (size_t)world * sizeof(void*)) != cudaSuccess ||
+      cudaMalloc(&ex->local, ex->block_words * 8) != cudaSuccess || cudaMalloc(&ex->counter, 4) != cudaSuccess) {
     delete ex;
     return abi_set_err(FRS_E_CUDA, "exchange buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   EX_TRY(cudaMemset(ex->gather, 0, gbytes));
   EX_TRY(cudaMemset(ex->flags, 0, (size_t)world * 4));
+  EX_TRY(cudaMemset(ex->counter, 0, 4));
   EX_TRY(cudaDeviceSynchronize());
   *out = ex;
   return FRS_OK;
@@ -122,6 +115,8 @@ extern "C" int frs_exchange_destroy(frs_exchange* ex) {
   cudaFree(ex->flags);
   cudaFree(ex->d_peer_gather);
   cudaFree(ex->d_peer_flags);
+  cudaFree(ex->local);
+  cudaFree(ex->counter);
   delete ex;
   return FRS_OK;
 }

@@ -11,6 +11,7 @@
 #include <new>
 
 #include "../../include/frs_b200.h"
+#include "exchange.cuh"
 #include "scan.cuh"
 
 using namespace frs;
@@ -450,7 +451,7 @@ static int scan_grid(const frs_index* ix, uint32_t num_tiles) {
 // prep -> scan -> merge on `st`.  Exactly one of (out_s32) / (out_s64) may be null.
 static int search_impl(frs_index* ix, const float* q, const uint32_t* code, const uint32_t* mask, int nq,
                        int k, float* out_s32, double* out_s64, int64_t* out_ids, cudaStream_t st,
-                       const uint32_t* tile_ids = nullptr, int64_t n_tile_ids = 0) {
+                       const uint32_t* tile_ids = nullptr, int64_t n_tile_ids = 0, frs_exchange* push = nullptr) {
   if (!ix) return set_err(FRS_E_INVALID, "idx is null");
   if (nq < 1 || nq > kNQ) return set_err(FRS_E_INVALID, "nq must be in [1,%d] (got %d)", kNQ, nq);
   if (k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "k must be in [1,%d] (got %d)", kMaxK, k);
@@ -521,6 +522,17 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
   mp.out_s32 = out_s32;
   mp.out_ids = out_ids;
   mp.stats = ix->stats;
+  if (push) {  // the exchange step rides in the tail of the merge kernel
+    ++push->seq;
+    mp.push.peer_gather = push->d_peer_gather;
+    mp.push.peer_flags = push->d_peer_flags;
+    mp.push.counter = push->counter;
+    mp.push.world = push->world;
+    mp.push.rank = push->rank;
+    mp.push.seq = push->seq;
+    mp.push.block_words = push->block_words;
+    mp.push.nq_stride = push->nq_max;
+  }
   CU_TRY(launch_merge(f32, mp, st));
   launches++;
   if (pev) {
@@ -557,6 +569,21 @@ extern "C" int frs_index_search_local(frs_index* idx, const float* dev_queries, 
   if (!dev_out_scores64) return set_err(FRS_E_INVALID, "null pointer argument");
   return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, nullptr, dev_out_scores64, dev_out_ids,
                      (cudaStream_t)stream);
+}
+
+// Local pass of the sharded search WITH the exchange push fused into the merge kernel: the shard's exact top-k
+// goes into the exchange's local block and, from the same kernel, into every peer's gather buffer.  Follow with
+// frs_exchange_wait_merge.  nq and k must be the ones the exchange was created with.
+extern "C" int frs_index_search_push(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
+                                     const uint32_t* dev_q_mask, int nq, int k, frs_exchange* ex, void* stream) {
+  if (!ex) return set_err(FRS_E_INVALID, "null pointer argument");
+  if (!ex->connected) return set_err(FRS_E_INVALID, "exchange is not connected");
+  if (nq != ex->nq_max || k != ex->k_max)
+    return set_err(FRS_E_INVALID, "nq / k (%d / %d) differ from the exchange's (%d / %d)", nq, k, ex->nq_max, ex->k_max);
+  if (idx && idx->device != ex->device) return set_err(FRS_E_INVALID, "index and exchange live on different devices");
+  const size_t plane = (size_t)nq * k;
+  return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, nullptr, reinterpret_cast<double*>(ex->local),
+                     reinterpret_cast<int64_t*>(ex->local) + plane, (cudaStream_t)stream, nullptr, 0, ex);
 }
 
 extern "C" int frs_index_search_host(frs_index* idx, const float* host_queries, const uint32_t* host_q_code,

@@ -903,6 +903,34 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
     if (p.out_s32) p.out_s32[o] = -INFINITY;
     p.out_ids[o] = -1;
   }
+  if (p.push.peer_gather) {
+    // Exchange step fused into this kernel: this query's k (fp64 score, id) words go straight into slot `rank`
+    // of every peer's gather buffer over NVLink peer memory (plain stores through IPC-mapped pointers).
+    __syncthreads();  // this CTA's results are in p.out_s64 / p.out_ids
+    const PushTarget& t = p.push;
+    const size_t plane = (size_t)t.nq_stride * k;
+    const size_t slot = ((size_t)(t.seq & 1u) * t.world + t.rank) * t.block_words;
+    const uint64_t* s64 = reinterpret_cast<const uint64_t*>(p.out_s64);
+    const uint64_t* ids = reinterpret_cast<const uint64_t*>(p.out_ids);
+    for (uint32_t i = tid; i < (uint32_t)(t.world * 2 * k); i += kMergeThreads) {
+      const uint32_t peer = i / (2 * k), w = i % (2 * k), pl = w / k, r = w % k;
+      const size_t o = (size_t)q * k + r;
+      t.peer_gather[peer][slot + pl * plane + o] = pl ? ids[o] : s64[o];
+    }
+    __syncthreads();
+    __shared__ unsigned int s_last;
+    if (tid == 0) {
+      __threadfence_system();  // cumulative: the CTA's stores (ordered before it by the barrier) are visible
+                               // system-wide before this CTA is counted
+      s_last = atomicAdd(t.counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {  // every other CTA has fenced its stores and been counted: publish the sequence number
+      if (tid == 0) *t.counter = 0;  // next launch (stream-ordered)
+      for (uint32_t peer = tid; peer < (uint32_t)t.world; peer += kMergeThreads)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flags[peer] + t.rank), "r"(t.seq) : "memory");
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

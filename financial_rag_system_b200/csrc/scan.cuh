@@ -56,6 +56,19 @@ struct ScanParams {
   unsigned long long* timeline;  // diagnostics: [grid, 8] globaltimer stamps, or null
 };
 
+// Peer-memory push fused into the tail of the merge kernel (csrc/exchange.cu): every query's CTA copies its k
+// (score, id) words into slot `rank` of every peer's gather buffer; the last CTA to finish publishes `seq` in
+// every peer's flag word.
+struct PushTarget {
+  uint64_t* const* peer_gather;  // device array [world], null = no push
+  uint32_t* const* peer_flags;   // device array [world]
+  unsigned int* counter;         // CTAs done (local, self-resetting)
+  int world, rank;
+  uint32_t seq;
+  size_t block_words;            // 2 * nq_max * k_max
+  int nq_stride;                 // nq_max of the exchange (plane = nq_max * k)
+};
+
 struct MergeParams {
   const uint64_t* part_keys;
   const uint32_t* part_cnt;
@@ -71,6 +84,7 @@ struct MergeParams {
   float* out_s32;      // [nq, k] or null
   int64_t* out_ids;    // [nq, k]
   unsigned long long* stats;
+  PushTarget push;
 };
 
 size_t scan_smem_bytes(bool f32);

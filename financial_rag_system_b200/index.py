@@ -194,6 +194,13 @@ class VectorIndex:
         check(self._lib.frs_index_search_local(self._h, _ptr(q), _ptr(qc), _ptr(qm), q.shape[0], k,
                                                _ptr(out_scores64), _ptr(out_ids), _stream_ptr(self.device)))
 
+    def search_push(self, q: torch.Tensor, qc: torch.Tensor, qm: torch.Tensor, k: int, exchange) -> None:
+        """Shard-local pass whose merge kernel also pushes the result into every peer's gather buffer
+        (frs_index_search_push); `exchange` is a sharded.PeerExchange created for (len(q), k)."""
+        self._check_batch(q.shape[0], k)
+        check(self._lib.frs_index_search_push(self._h, _ptr(q), _ptr(qc), _ptr(qm), q.shape[0], k, exchange._h,
+                                              _stream_ptr(self.device)))
+
     def last_queries(self) -> torch.Tensor:
         out = torch.empty((FRS_MAX_BATCH, FRS_DIM), dtype=torch.float32, device=self.device)
         check(self._lib.frs_index_last_queries(self._h, _ptr(out), _stream_ptr(self.device)))

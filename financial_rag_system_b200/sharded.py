@@ -159,14 +159,13 @@ class ShardedIndex:
             self._bufs[key] = (loc, gat)
         return self._bufs[key]
 
+    def _peer_exchange(self, nq: int, k: int) -> "PeerExchange":
+        key = (nq, k)
+        if key not in self._peer:  # collective on first use: every rank creates and connects it
+            self._peer[key] = PeerExchange(self.device, self.world, self.rank, nq, k, group=self.group)
+        return self._peer[key]
+
     def _exchange_and_merge(self, loc: torch.Tensor, gat: torch.Tensor, k: int):
-        if self.exchange == "p2p":
-            key = (loc.shape[1], k)
-            if key not in self._peer:  # collective on first use: every rank creates and connects it
-                self._peer[key] = PeerExchange(self.device, self.world, self.rank, loc.shape[1], k, group=self.group)
-            ex = self._peer[key]
-            ex.push(loc)
-            return ex.wait_merge()
         if self.world > 1:
             # output viewed as the concatenation of the per-rank inputs along dim 0 (what gloo expects;
             # NCCL accepts both forms)
@@ -183,6 +182,11 @@ class ShardedIndex:
         """Synchronous-in-stream sharded search; every rank must call it with the same queries.
         Returns (ids int64 [nq,k] global, scores float32 [nq,k]) on every rank."""
         q, qc, qm = self._prep(queries, q_code, q_mask)
+        if self.exchange == "p2p":
+            # the local merge kernel writes the shard's top-k into every peer's gather buffer itself
+            ex = self._peer_exchange(q.shape[0], k)
+            self.local.search_push(q, qc, qm, k, ex)
+            return ex.wait_merge()
         loc, gat = self._buffers(q.shape[0], k, 0)
         self._local_pass(q, qc, qm, k, loc)
         return self._exchange_and_merge(loc, gat, k)
@@ -194,10 +198,21 @@ class ShardedIndex:
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
         q, qc, qm = self._prep(queries, q_code, q_mask)
+        main = torch.cuda.current_stream(self.device)
+        if self.exchange == "p2p":
+            ex = self._peer_exchange(q.shape[0], k)
+            self.local.search_push(q, qc, qm, k, ex)  # local pass + push, on the caller's stream
+            done_local = torch.cuda.Event()
+            done_local.record(main)
+            with torch.cuda.stream(self._side):  # wait for the peers + final merge overlap the next local pass
+                self._side.wait_event(done_local)
+                ids, scores = ex.wait_merge()
+                ready = torch.cuda.Event()
+                ready.record(self._side)
+            return PendingSearch(ids, scores, ready)
         slot = self._slot
         self._slot ^= 1
         loc, gat = self._buffers(q.shape[0], k, slot)
-        main = torch.cuda.current_stream(self.device)
         # the buffers of this slot were last used two calls ago on the side stream
         if self._slot_free[slot] is not None:
             main.wait_event(self._slot_free[slot])

@@ -170,6 +170,10 @@ int frs_exchange_connect(frs_exchange* ex, const uint8_t* handles_world_by_128);
 int frs_exchange_connect_local(frs_exchange* ex, frs_exchange* const* peers);
 int frs_exchange_push(frs_exchange* ex, const int64_t* dev_local_packed, void* stream);
 int frs_exchange_wait_merge(frs_exchange* ex, float* dev_out_scores, int64_t* dev_out_ids, void* stream);
+/* the local pass with the push FUSED into its merge kernel (one CTA per query writes its k results into every
+ * peer's gather buffer, the last CTA publishes the flags): replaces frs_index_search_local + frs_exchange_push */
+int frs_index_search_push(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
+                          const uint32_t* dev_q_mask, int nq, int k, frs_exchange* ex, void* stream);
 
 /* the prepared (normalised, storage-dtype-rounded) queries of the last search,
  * widened to fp32: what the scores are dot products with.  [FRS_MAX_BATCH, 384] */

@@ -287,9 +287,12 @@ def test_peer_memory_exchange_equals_one_index():
         qc = _i32((codes[batch * 32:batch * 32 + nq] & 0x7FFFFFFF).cpu().numpy())
         qm = _i32(np.full(nq, TICKER, np.uint32))
         for r in range(3):  # all pushes first: the waits of one process would otherwise wait for each other
-            loc = torch.empty((2, nq, k), dtype=torch.int64, device="cuda")
-            shards[r].search_local(q, qc, qm, k, loc[0].view(torch.float64), loc[1])
-            exs[r].push(loc)
+            if batch % 2 == 0:  # the push fused into the local merge kernel (frs_index_search_push)
+                shards[r].search_push(q, qc, qm, k, exs[r])
+            else:               # the stand-alone push of an existing block
+                loc = torch.empty((2, nq, k), dtype=torch.int64, device="cuda")
+                shards[r].search_local(q, qc, qm, k, loc[0].view(torch.float64), loc[1])
+                exs[r].push(loc)
         wi, ws = whole.search(q, qc, qm, k)
         for r in range(3):
             mi, ms = exs[r].wait_merge()
