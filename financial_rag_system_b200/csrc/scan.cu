@@ -922,7 +922,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
     if (tid == 0) {
       __threadfence_system();  // cumulative: the CTA's stores (ordered before it by the barrier) are visible
                                // system-wide before this CTA is counted
-      s_last = atomicAdd(t.counter, 1u) == gridDim.x - 1;
+      const bool last = atomicAdd(t.counter, 1u) == gridDim.x - 1;
+      if (last) __threadfence_system();  // acquire side: the other CTAs' fenced stores precede the flag stores below
+      s_last = last;
     }
     __syncthreads();
     if (s_last) {  // every other CTA has fenced its stores and been counted: publish the sequence number
