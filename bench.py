@@ -216,8 +216,11 @@ def workload_config(n_gpus):
         "filter": f"ticker == T, T ~ Zipf(1.1) over {N_TICKERS} tickers (reference main.py:218-223)",
         "corpus": "1024 unit centroids + noise of norm 0.3, L2-normalised, generated on device (seed 7)",
         "parallelism": (f"rows sharded over {n_gpus} GPU(s); exchange of the 32x15 (score,id) lists per batch: "
-                        + ("NCCL all-gather" if os.environ.get("FRS_EXCHANGE", "p2p").lower() == "nccl"
-                           else "stores into the peers' buffers over NVLink peer memory + flags (csrc/exchange.cu)")) if n_gpus > 1 else "1 GPU",
+                        + {"nccl": "NCCL all-gather",
+                           "p2p": "stores into the peers' buffers over NVLink peer memory + flags, fused into the local merge kernel",
+                           "auto": "value (pipelined search_async): NCCL all-gather hidden on a side stream; e2e (synchronous "
+                                   "search): stores into the peers' buffers over NVLink peer memory, fused into the local merge kernel"}
+                        [os.environ.get("FRS_EXCHANGE", "auto").lower()]) if n_gpus > 1 else "1 GPU",
         "l2": "inputs larger than L2 (7.7 GB corpus per step vs 126 MB L2)",
     }
 
@@ -302,7 +305,7 @@ def run_ours(args):
         seg_ids, _ = ix.search_tiles(q, qc, qm, K, tiles_dev)
         assert torch.equal(full_ids, seg_ids), "restricted scan must return the ids of the full scan"
 
-    if sh is not None and sh.exchange == "p2p":
+    if sh is not None and sh.exchange in ("p2p", "auto"):
         # the peer-memory exchange must return exactly what the NCCL all-gather form returns
         ref = ShardedIndex(ix, rank, world, exchange="nccl")
         pi, ps = sh.search(q, qc, qm, K)

@@ -14,10 +14,10 @@
 // The data crosses NVSwitch exactly once per (source, destination) pair, no kernel of a collective library has to be
 // resident next to the persistent scan kernel, and the latency is one store + one flag per peer.
 //
-// Buffer reuse: gather buffers are double-buffered by sequence parity.  A peer can push sequence s + 2 (same slot
-// as s) only after it has merged s + 1, which needs THIS rank's push of s + 1, which this rank issues (stream
-// order) after its own merge of s — so a slot is never overwritten while it is being read.  Flags are monotonic
-// (no reset, no ABA).
+// Buffer reuse: gather buffers are a ring of kExchangeSlots = 4 batches (scan.cuh): a rank may issue the push of
+// batch t + 2 only after its own final merge of batch t (ShardedIndex.search_async orders its streams that way; the
+// synchronous form pushes t + 1 after merging t), which keeps a slot from being overwritten while a peer still
+// reads it.  Flags are monotonic (no reset, no ABA).
 //
 // The reference has no counterpart (one Qdrant server, main.py:215-239); this is north-star item (3), the exchange
 // step of `ShardedIndex` (sharded.py).
@@ -37,6 +37,7 @@ namespace frs {
 int abi_set_err(int code, const char* fmt, ...);
 }
 using frs::abi_set_err;
+using frs::kExchangeSlots;
 
 #define EX_TRY(expr)                                                                                              \
   do {                                                                                                            \
@@ -53,7 +54,7 @@ exchange_push_kernel(const uint64_t* __restrict__ local, uint64_t* const* __rest
                      uint32_t* const* __restrict__ peer_flags, int world, int rank, uint32_t words,
                      size_t block_words, uint32_t seq) {
   const int peer = blockIdx.x;
-  uint64_t* dst = peer_gather[peer] + ((size_t)(seq & 1u) * world + rank) * block_words;
+  uint64_t* dst = peer_gather[peer] + ((size_t)(seq % kExchangeSlots) * world + rank) * block_words;
   for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = local[i];
   __threadfence_system();  // the payload is visible system-wide before the flag
   __syncthreads();
@@ -89,7 +90,7 @@ extern "C" int frs_exchange_create(int device, int world, int rank, int nq_max, 
   ex->nq_max = nq_max;
   ex->k_max = k_max;
   ex->block_words = 2 * (size_t)nq_max * k_max;
-  const size_t gbytes = 2 * (size_t)world * ex->block_words * 8;
+  const size_t gbytes = (size_t)kExchangeSlots * world * ex->block_words * 8;
   // plain cudaMalloc (not a caching-allocator sub-block): the IPC handle names exactly this allocation
   if (cudaMalloc(&ex->gather, gbytes) != cudaSuccess || cudaMalloc(&ex->flags, (size_t)world * 4) != cudaSuccess ||
       cudaMalloc(&ex->d_peer_gather, (size_t)world * sizeof(void*)) != cudaSuccess ||
@@ -203,7 +204,7 @@ extern "C" int frs_exchange_wait_merge(frs_exchange* ex, float* dev_out_scores, 
   cudaStream_t st = (cudaStream_t)stream;
   exchange_wait_kernel<<<1, 64, 0, st>>>(ex->flags, ex->world, ex->seq);
   EX_TRY(cudaGetLastError());
-  const uint64_t* slot = ex->gather + (size_t)(ex->seq & 1u) * ex->world * ex->block_words;
+  const uint64_t* slot = ex->gather + (size_t)(ex->seq % kExchangeSlots) * ex->world * ex->block_words;
   const size_t plane = (size_t)ex->nq_max * ex->k_max;
   EX_TRY(frs::launch_merge_shards(reinterpret_cast<const double*>(slot), reinterpret_cast<const int64_t*>(slot) + plane,
                                   ex->world, ex->nq_max, ex->k_max, 2 * plane, dev_out_scores, dev_out_ids, st));

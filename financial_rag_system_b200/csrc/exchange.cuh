@@ -7,7 +7,7 @@
 struct frs_exchange {
   int device = 0, world = 1, rank = 0, nq_max = 0, k_max = 0;
   size_t block_words = 0;             // 2 * nq_max * k_max 64-bit words per (slot, source rank)
-  uint64_t* gather = nullptr;         // [2 slots][world][block_words]   (local, written by the peers)
+  uint64_t* gather = nullptr;         // [kExchangeSlots][world][block_words]   (local, written by the peers)
   uint32_t* flags = nullptr;          // [world]: last sequence number pushed by each rank (local, written by peers)
   uint64_t** d_peer_gather = nullptr; // device array [world]: every rank's gather buffer as seen from this GPU
   uint32_t** d_peer_flags = nullptr;  // device array [world]

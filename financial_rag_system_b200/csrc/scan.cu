@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
     __syncthreads();  // this CTA's results are in p.out_s64 / p.out_ids
     const PushTarget& t = p.push;
     const size_t plane = (size_t)t.nq_stride * k;
-    const size_t slot = ((size_t)(t.seq & 1u) * t.world + t.rank) * t.block_words;
+    const size_t slot = ((size_t)(t.seq % kExchangeSlots) * t.world + t.rank) * t.block_words;
     const uint64_t* s64 = reinterpret_cast<const uint64_t*>(p.out_s64);
     const uint64_t* ids = reinterpret_cast<const uint64_t*>(p.out_ids);
     for (uint32_t i = tid; i < (uint32_t)(t.world * 2 * k); i += kMergeThreads) {

@@ -59,6 +59,13 @@ struct ScanParams {
 // Peer-memory push fused into the tail of the merge kernel (csrc/exchange.cu): every query's CTA copies its k
 // (score, id) words into slot `rank` of every peer's gather buffer; the last CTA to finish publishes `seq` in
 // every peer's flag word.
+// Gather buffers are a ring of kExchangeSlots batches.  Rule for the callers: a rank issues the push of batch t + d
+// only after its own final merge of batch t.  A peer's push of s + D lands on slot s; it comes after the peer's merge
+// of s + D - d, which needed this rank's push of s + D - d, issued after this rank's merge of s + D - 2d: D >= 2d keeps
+// a slot from being overwritten while it is read.  d = 2 (one batch of overlap between a local pass and the previous
+// batch's wait + merge on a side stream) needs D = 4.
+constexpr uint32_t kExchangeSlots = 4;
+
 struct PushTarget {
   uint64_t* const* peer_gather;  // device array [world], null = no push
   uint32_t* const* peer_flags;   // device array [world]
