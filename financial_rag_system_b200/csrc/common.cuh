@@ -123,26 +123,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
-}
-// arrive on a peer CTA's mbarrier; release at cluster scope orders this thread's earlier DSMEM stores
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
-}
 // arrive on a peer CTA's mbarrier WITHOUT a cluster-scope release of this thread's memory operations: for signals
 // whose payload is not generic memory (a drained TMEM accumulator, ordered by tcgen05.wait::ld + tcgen05.fence).
 // (The .release.cluster form above costs ~1 us per call: measured 1056 ns against 128 ns for a local arrive.)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
-}
-// 8-byte store into a peer CTA's shared memory that completes bytes on an mbarrier of that CTA: the data carries
-// its own completion, no release fence in the sending thread
-__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
-                   cluster_addr),
-               "f"(a), "f"(b), "r"(cluster_bar_addr)
-               : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -289,17 +274,6 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Same for the SWIZZLE_64B layout (rows 64 B wide, 8-row groups 512 B apart): head_dim 32 x bf16.
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
-  return d;
-}
-
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.
 //   fmt: 1 = bf16, 0 = f16, 2 = tf32
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
@@ -333,18 +307,6 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
   }
 }
 
-// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (lane = row, two bf16 K-values
-// per 32-bit column), so a matrix produced by the threads (softmax probabilities) never touches shared memory
-__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // 1 in exactly one lane of the (converged) warp, chosen by the hardware: elect.sync
 __device__ __forceinline__ uint32_t elect_one_pred() {
   uint32_t pred;
@@ -369,6 +331,8 @@ __device__ __forceinline__ void tc_mma_f16_pred(uint32_t tmem_d, uint64_t desc_a
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (lane = row, two bf16 K-values
+// per 32-bit column), so a matrix produced by the threads (softmax probabilities) never touches shared memory
 __device__ __forceinline__ void tc_mma_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate, uint32_t issue) {
   asm volatile(
