@@ -238,6 +238,14 @@ class ShardedIndex:
         self._slot_free[slot] = ready
         return PendingSearch(ids, scores, ready)
 
+    def close(self) -> None:
+        """Releases the peer-memory exchanges (IPC mappings, gather buffers).  The local index stays open."""
+        if self._side is not None:
+            self._side.synchronize()
+        for ex in self._peer.values():
+            ex.close()
+        self._peer = {}
+
     def _prep(self, queries, q_code, q_mask):
         q = torch.as_tensor(queries).to(device=self.device, dtype=torch.float32).contiguous()
         qc = torch.as_tensor(q_code).to(device=self.device)
