@@ -80,3 +80,16 @@ def test_two_rank_gloo_search_equals_single_shard(tmp_path):
         assert np.array_equal(got["ids"], want_i)
         assert np.allclose(got["scores"], want_s, atol=1e-6)
     assert want_i[0][:2].tolist() == [3, 500]  # the cross-shard duplicate ties in id order
+
+
+def test_exchange_selection_without_cuda():
+    """The peer-memory exchange is a CUDA path: with injected hooks (the gloo test above) or one shard the index
+    uses the collective form whatever was asked for; an unknown name is rejected."""
+    import pytest
+
+    noop = lambda *a: None  # noqa: E731
+    for asked in (None, "auto", "p2p", "nccl"):
+        sh = ShardedIndex(object(), 0, 2, local_search=noop, merge=noop, device=torch.device("cpu"), exchange=asked)
+        assert sh.exchange == "nccl"
+    with pytest.raises(ValueError):
+        ShardedIndex(object(), 0, 2, local_search=noop, merge=noop, device=torch.device("cpu"), exchange="mpi")
