@@ -59,16 +59,35 @@ class PeerExchange:
         self._lib, self._C = _lib, C
         self.device, self.world, self.rank, self.nq, self.k = device, int(world), int(rank), int(nq), int(k)
         h = C.c_void_p()
-        _lib.check(_lib.lib().frs_exchange_create(device.index or 0, self.world, self.rank, self.nq, self.k, C.byref(h)))
-        self._h = h
-        if connect:
-            buf = (C.c_uint8 * 128)()
+        if not connect:
+            _lib.check(_lib.lib().frs_exchange_create(device.index or 0, self.world, self.rank, self.nq, self.k, C.byref(h)))
+            self._h = h
+            return
+        # Collective set-up: every rank takes part in the handle all-gather and in the final agreement even if one
+        # of its own steps failed (CUDA IPC can be unavailable, e.g. in a restricted container), so that no rank is
+        # left waiting in a collective and all ranks reach the same verdict.
+        self._h, err = None, None
+        buf = (C.c_uint8 * 128)()
+        try:
+            _lib.check(_lib.lib().frs_exchange_create(device.index or 0, self.world, self.rank, self.nq, self.k, C.byref(h)))
+            self._h = h
             _lib.check(_lib.lib().frs_exchange_handle(self._h, buf))
-            mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
-            every = torch.empty(self.world * 128, dtype=torch.uint8, device=device)
-            dist.all_gather_into_tensor(every, mine, group=group)
-            raw = bytes(every.cpu().numpy().tobytes())
-            _lib.check(_lib.lib().frs_exchange_connect(self._h, C.cast(C.c_char_p(raw), C.c_void_p)))
+        except Exception as e:  # noqa: BLE001
+            err = e
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        every = torch.empty(self.world * 128, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        if err is None:
+            try:
+                raw = bytes(every.cpu().numpy().tobytes())
+                _lib.check(_lib.lib().frs_exchange_connect(self._h, C.cast(C.c_char_p(raw), C.c_void_p)))
+            except Exception as e:  # noqa: BLE001
+                err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer-memory exchange unavailable on at least one rank (this rank: {err})")
 
     @staticmethod
     def link(exchanges) -> None:
@@ -96,7 +115,7 @@ class PeerExchange:
         return out_i, out_s
 
     def close(self) -> None:
-        if self._h is not None:
+        if getattr(self, "_h", None) is not None:
             self._lib.lib().frs_exchange_destroy(self._h)
             self._h = None
 
@@ -163,10 +182,21 @@ class ShardedIndex:
             self._bufs[key] = (loc, gat)
         return self._bufs[key]
 
-    def _peer_exchange(self, nq: int, k: int) -> "PeerExchange":
+    def _peer_exchange(self, nq: int, k: int) -> Optional["PeerExchange"]:
+        """Collective on first use: every rank creates and connects it.  In "auto" mode a set-up that fails on any
+        rank (no CUDA IPC) switches every rank to the all-gather form — both are GPU paths; "p2p" raises."""
         key = (nq, k)
-        if key not in self._peer:  # collective on first use: every rank creates and connects it
-            self._peer[key] = PeerExchange(self.device, self.world, self.rank, nq, k, group=self.group)
+        if key not in self._peer:
+            try:
+                self._peer[key] = PeerExchange(self.device, self.world, self.rank, nq, k, group=self.group)
+            except RuntimeError as e:
+                if self.exchange != "auto":
+                    raise
+                import warnings
+
+                warnings.warn(f"{e}; using the NCCL all-gather exchange")
+                self.exchange = "nccl"
+                return None
         return self._peer[key]
 
     def _exchange_and_merge(self, loc: torch.Tensor, gat: torch.Tensor, k: int):
@@ -186,9 +216,9 @@ class ShardedIndex:
         """Synchronous-in-stream sharded search; every rank must call it with the same queries.
         Returns (ids int64 [nq,k] global, scores float32 [nq,k]) on every rank."""
         q, qc, qm = self._prep(queries, q_code, q_mask)
-        if self.exchange in ("p2p", "auto"):
+        ex = self._peer_exchange(q.shape[0], k) if self.exchange in ("p2p", "auto") else None
+        if ex is not None:
             # the local merge kernel writes the shard's top-k into every peer's gather buffer itself
-            ex = self._peer_exchange(q.shape[0], k)
             self.local.search_push(q, qc, qm, k, ex)
             return ex.wait_merge()
         loc, gat = self._buffers(q.shape[0], k, 0)
