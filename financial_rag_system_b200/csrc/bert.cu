@@ -678,7 +678,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       } else {
         // LayerNorm over the 384-wide row: this thread owns 192 columns of its row, the thread of the other
         // column-half group (same lane quarter) the other 192.  Pass 1: bias (the residual is already in the
-        // accumulator), row statistics, pre-LayerNorm value back to TMEM (fp32).
+        // accumulator) and row statistics; pass 2 reads the accumulator again and repeats the one bias FADD2 per
+        // pair (bit-identical), which is cheaper than writing the pre-LayerNorm value back to TMEM in between.
         float sum = 0.f, sq = 0.f, sum1 = 0.f, sq1 = 0.f;  // even / odd columns (packed pairs)
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
@@ -693,12 +694,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             fadd2(a, b, bb.x, bb.y);
             fadd2(sum, sum1, a, b);
             ffma2_acc(sq, sq1, a, b, a, b);
-            v[2 * j] = __float_as_uint(a);
-            v[2 * j + 1] = __float_as_uint(b);
           }
-          tmem_st_32x32(taddr + c * 32, v);
         }
-        tmem_st_wait();
         FRS_GT(17);
         sum += sum1;
         sq += sq1;
@@ -727,10 +724,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            // ((v - mean) * rstd) * gamma + beta on the packed pipes
+            // (((v + bias) - mean) * rstd) * gamma + beta on the packed pipes
             float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+            const float2 bb = *reinterpret_cast<const float2*>(sbias + col + 2 * j);
             const float2 gg = *reinterpret_cast<const float2*>(sgamma + col + 2 * j);
             const float2 be = *reinterpret_cast<const float2*>(sbeta + col + 2 * j);
+            fadd2(a, b, bb.x, bb.y);
             fadd2(a, b, -mean, -mean);
             fmul2(a, b, rstd, rstd);
             ffma2(a, b, gg.x, gg.y, be.x, be.y);
