@@ -188,7 +188,7 @@ def run_reference(args):
     rows, codes, queries, qt = cpu_sample_data(50_000)
     per_row = cpu_step_time(rows, codes, queries, qt, 1, 1) / 50_000
     budget_s = 150.0
-    sample_rows = int(min(CPU_SAMPLE_ROWS, max(50_000, budget_s / ((args.steps + args.warmup) * per_row))))
+    sample_rows = int(min(CPU_SAMPLE_ROWS, TOTAL_ROWS, max(50_000, budget_s / ((args.steps + args.warmup) * per_row))))
     rows, codes, queries, qt = cpu_sample_data(sample_rows)
     t = cpu_step_time(rows, codes, queries, qt, args.steps, args.warmup)
     scale = TOTAL_ROWS / sample_rows
