@@ -216,6 +216,8 @@ class ShardedIndex:
         """Synchronous-in-stream sharded search; every rank must call it with the same queries.
         Returns (ids int64 [nq,k] global, scores float32 [nq,k]) on every rank."""
         q, qc, qm = self._prep(queries, q_code, q_mask)
+        if self._side is not None:  # after pipelined calls: their exchanges come first (sequence numbers, slots)
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
         ex = self._peer_exchange(q.shape[0], k) if self.exchange in ("p2p", "auto") else None
         if ex is not None:
             # the local merge kernel writes the shard's top-k into every peer's gather buffer itself
@@ -233,24 +235,6 @@ class ShardedIndex:
             self._side = torch.cuda.Stream(device=self.device)
         q, qc, qm = self._prep(queries, q_code, q_mask)
         main = torch.cuda.current_stream(self.device)
-        if self.exchange == "p2p":
-            ex = self._peer_exchange(q.shape[0], k)
-            # ring of 4 gather slots (csrc/scan.cuh kExchangeSlots): the push of batch t + 2 must come after this
-            # rank's own final merge of batch t, or a fast rank overwrites a slot a slow peer still reads
-            self._p2p_ready = getattr(self, "_p2p_ready", [])
-            if len(self._p2p_ready) >= 2:
-                main.wait_event(self._p2p_ready[-2])
-                self._p2p_ready = self._p2p_ready[-2:]
-            self.local.search_push(q, qc, qm, k, ex)  # local pass + push, on the caller's stream
-            done_local = torch.cuda.Event()
-            done_local.record(main)
-            with torch.cuda.stream(self._side):  # wait for the peers + final merge overlap the next local pass
-                self._side.wait_event(done_local)
-                ids, scores = ex.wait_merge()
-                ready = torch.cuda.Event()
-                ready.record(self._side)
-            self._p2p_ready.append(ready)
-            return PendingSearch(ids, scores, ready)
         slot = self._slot
         self._slot ^= 1
         loc, gat = self._buffers(q.shape[0], k, slot)
@@ -260,9 +244,18 @@ class ShardedIndex:
         self._local_pass(q, qc, qm, k, loc)
         done_local = torch.cuda.Event()
         done_local.record(main)
+        # "p2p": the stand-alone push of the finished block + wait + merge, all on the side stream (the push of
+        # batch t + 1 is stream-ordered behind this rank's merge of batch t, the d = 1 case of the slot rule in
+        # csrc/scan.cuh).  The push FUSED into the merge kernel would sit on the caller's stream in front of the
+        # next scan (8 GPUs: 137 k against 181 k QPS), so the pipelined form does not use it.
+        ex = self._peer_exchange(q.shape[0], k) if self.exchange == "p2p" else None
         with torch.cuda.stream(self._side):
             self._side.wait_event(done_local)
-            ids, scores = self._exchange_and_merge(loc, gat, k)
+            if ex is not None:
+                ex.push(loc)
+                ids, scores = ex.wait_merge()
+            else:
+                ids, scores = self._exchange_and_merge(loc, gat, k)
             ready = torch.cuda.Event()
             ready.record(self._side)
         self._slot_free[slot] = ready
