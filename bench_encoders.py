@@ -103,19 +103,86 @@ def cpu_encode_rate(workload, seconds_budget=20.0):
                               "sentence-transformers itself is not installed (it calls this module)"}
 
 
+def cpu_pipeline_config1(rounds: int = 2):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: 10k synthetic SEC chunks, bge-small-shaped
+    query embedding, exact top-15 with ticker filter (numpy restatement of qdrant-client :memory:), MiniLM-L-6-shaped
+    cross-encoder rerank to top-5 — for 10 CONCURRENT queries (load_testing.py:173-200 drives 10 users; main.py:211-247 is
+    the per-request path: embed_query -> retrieve_from_qdrant -> rerank_documents), transformers fp32 on the host cores.
+    The 10k stored vectors are not embedded on the CPU (that would take ~10 minutes and is ingest, not the request
+    path): 64 chunks are embedded for real, the rest are seeded unit vectors; every chunk has real text for the reranker."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    from financial_rag_system_b200 import synth
+    from financial_rag_system_b200.checkpoint import BGE_SMALL, MINILM_L6_CE, synthetic_checkpoint
+    from financial_rag_system_b200.tokenizer import WordPiece
+    from oracle import encoder_oracle as eo
+    from oracle import search_oracle as so
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    n_rows, n_users = 10_000, 10
+    tok = WordPiece.synthetic()   # the `tokenizers` WordPiece the reference's models use, synthetic vocabulary
+    emb = eo.hf_model(BGE_SMALL, synthetic_checkpoint(BGE_SMALL, 1234))
+    ce = eo.hf_model(MINILM_L6_CE, synthetic_checkpoint(MINILM_L6_CE, 4321))
+    _, texts, payloads = synth.make_chunks(n_rows, seed=1234)
+    rng = np.random.default_rng(1234)
+    vecs = so.l2_normalize_f32(rng.standard_normal((n_rows, 384)).astype(np.float32))
+    ids64, cu64 = tok.pack_texts(texts[:64])
+    vecs[:64] = eo.hf_embed(emb, ids64, cu64)
+    tick = np.array([p["ticker"] for p in payloads])
+    queries, _ = synth.make_queries(n_users, seed=21)
+    q_tickers = [payloads[int(j)]["ticker"] for j in rng.integers(0, n_rows, n_users)]
+    stage = {"embed": [], "search": [], "rerank": []}
+    lock = threading.Lock()
+
+    def one_request(i):
+        t0 = time.perf_counter()
+        qi, qcu = tok.pack_texts([queries[i]])
+        v = eo.hf_embed(emb, qi, qcu)[0]                                   # main.py:211-213
+        t1 = time.perf_counter()
+        top, _ = so.as_shipped_search(vecs, v, tick == q_tickers[i], 15)   # main.py:215-239
+        t2 = time.perf_counter()
+        pairs = [[queries[i], texts[int(r)]] for r in top]
+        pi, pt, pcu = tok.pack_pairs(pairs)
+        scores = eo.hf_score_pairs(ce, pi, pt, pcu)                        # main.py:241-247
+        idx = np.argsort(scores)[::-1][:5]
+        t3 = time.perf_counter()
+        with lock:
+            stage["embed"].append(t1 - t0)
+            stage["search"].append(t2 - t1)
+            stage["rerank"].append(t3 - t2)
+        return idx
+
+    walls = []
+    for rd in range(rounds + 1):
+        for v_ in stage.values():
+            v_.clear()
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(n_users) as ex:
+            list(ex.map(one_request, range(n_users)))
+        if rd > 0:
+            walls.append(time.perf_counter() - t0)
+    wall = float(np.median(walls))
+    return {"value": n_users / wall, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"{n_users} concurrent requests (threads) over {n_rows} chunks, {rounds} timed rounds after one warm-up; transformers "
+                      f"BertModel-12 / BertForSequenceClassification-6 fp32 (seeded synthetic weights of the reference checkpoints' shapes) on "
+                      f"{cores} host threads; numpy restatement of qdrant-client exact search; sentence-transformers / qdrant-client "
+                      "themselves are not installed in this image",
+            "wall_s_per_round": wall,
+            "stage_ms_median_last_round": {k: float(np.median(v_) * 1e3) for k, v_ in stage.items()}}
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     t0 = time.perf_counter()
     w = args.workload
     if w == "pipeline":
-        # per 32-query batch: one embed call + 32 x (search + 15-pair rerank), as main2.py does it
-        r_e, _ = cpu_encode_rate("embed", 8.0)
-        r_r, cb = cpu_encode_rate("rerank", 12.0)
-        per_batch = NQ * 20 / (r_e * 512) + NQ * LIMIT / r_r  # queries are ~20 tokens: scale the 512-token rate
-        value = NQ / per_batch
-        cb = dict(cb, value=value, unit="queries/s",
-                  sample=cb["sample"] + f"; query embedding scaled from the 512-token rate; search over {PIPE_ROWS} rows is < 1% and omitted")
+        cb = cpu_pipeline_config1()   # the stated config: 10k chunks, 10 concurrent requests, embed -> search -> rerank
+        value = cb["value"]
     else:
         value, cb = cpu_encode_rate(w)
     line = {"impl": "reference", "metric": metric_name(w), "value": value, "unit": unit_name(w), "n_gpus": args.gpus,
@@ -129,29 +196,25 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def run_ours(args, ClockSampler, summarize_clocks):
+def measure(cx, w, steps, warmup, ClockSampler, summarize_clocks, with_cpu=True):
+    """One workload on the ranks of `cx` (bench.Ctx); returns the JSON line (rank 0) or None."""
     import torch
-    import torch.distributed as dist
 
     from financial_rag_system_b200 import synth
     from financial_rag_system_b200.encoder import Embedder, Reranker
     from financial_rag_system_b200.tokenizer import WordPiece
 
-    w = args.workload
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local_rank, dev = cx.rank, cx.world, cx.local_rank, cx.dev
+    dist = cx.dist
+    barrier = cx.barrier
     tok = WordPiece.synthetic()
     rng = np.random.default_rng(100 + rank)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    class _A:
+        pass
+
+    args = _A()
+    args.steps, args.warmup = steps, warmup
 
     retr = None
     if w == "embed":
@@ -295,7 +358,7 @@ def run_ours(args, ClockSampler, summarize_clocks):
                          "dominant_class": top, "step_flops": fl},
             "clocks": summarize_clocks(samples),
         }
-        if world == 1:
+        if world == 1 and with_cpu:
             if w == "pipeline":
                 r_e, _ = cpu_encode_rate("embed", 6.0)
                 r_r, cb = cpu_encode_rate("rerank", 10.0)
@@ -305,10 +368,34 @@ def run_ours(args, ClockSampler, summarize_clocks):
             else:
                 _, cb = cpu_encode_rate(w, 15.0)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     if retr is not None:
         retr.close()
     else:
         model.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def run_ours(args, ClockSampler, summarize_clocks, Ctx):
+    cx = Ctx(args)
+    line = measure(cx, args.workload, args.steps, args.warmup, ClockSampler, summarize_clocks)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
+
+
+def measure_compact(cx, w, ClockSampler, summarize_clocks, steps=None):
+    """The same measurement, boiled down for the `secondary` object of the headline line."""
+    steps = steps or {"embed": 10, "rerank": 10, "pipeline": 10}[w]
+    line = measure(cx, w, steps, 3, ClockSampler, summarize_clocks, with_cpu=cx.world == 1)
+    if line is None:
+        return None
+    out = {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": steps,
+           "e2e": line["e2e"]["value"], "frac_of_sustained_bf16": line["roofline"]["frac"], "achieved_tflops": line["roofline"]["achieved"],
+           "per_pass_kernel_class_ms": line["roofline"]["per_pass_kernel_class_ms"], "clocks": line["clocks"],
+           "workload": line["config"]["workload"], "n_gpus": line["n_gpus"]}
+    if "cpu_baseline" in line:
+        out["cpu_baseline"] = {k: line["cpu_baseline"][k] for k in ("value", "unit", "cores", "kind", "sample")}
+    return out

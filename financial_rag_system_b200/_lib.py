@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FRS_B200_LIB") or os.path.join(_HERE, "csrc", "libfrs_b200.so")
 
 FRS_OK = 0
+FRS_E_TIMEOUT = -5
 FRS_DTYPE_F32 = 0
 FRS_DTYPE_BF16 = 1
 FRS_DIM = 384
@@ -37,8 +38,10 @@ PROTOTYPES = {
     "frs_index_size": (_i64, [_vp]),
     "frs_index_capacity": (_i64, [_vp]),
     "frs_index_dtype": (_int, [_vp]),
+    "frs_index_device": (_int, [_vp]),
     "frs_index_set_base": (_int, [_vp, _i64]),
     "frs_index_set_scan_grid": (_int, [_vp, _int]),
+    "frs_index_set_pipeline_reserve": (_int, [_vp, _int]),
     "frs_index_add": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "frs_index_add_host": (_int, [_vp, _vp, _vp, _i64]),
     "frs_index_set_rows": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
@@ -53,6 +56,11 @@ PROTOTYPES = {
     "frs_index_search": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "frs_index_search_tiles": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _vp, _vp, _vp]),
     "frs_index_search_host": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "frs_index_search_async": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, C.POINTER(_int)]),
+    "frs_index_wait": (_int, [_vp, _int, _vp]),
+    "frs_index_sync": (_int, [_vp, _int]),
+    "frs_index_search_host_submit": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, C.POINTER(_int)]),
+    "frs_index_search_host_collect": (_int, [_vp, _vp, _int, _vp, _vp]),
     "frs_index_search_local": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "frs_merge_shards": (_int, [_int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
     "frs_merge_shards_packed": (_int, [_int, _vp, _int, _int, _int, _vp, _vp, _vp]),
@@ -63,12 +71,32 @@ PROTOTYPES = {
     "frs_exchange_connect_local": (_int, [_vp, _vp]),
     "frs_exchange_push": (_int, [_vp, _vp, _vp]),
     "frs_exchange_wait_merge": (_int, [_vp, _vp, _vp, _vp]),
+    "frs_exchange_wait_merge_n": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
+    "frs_exchange_set_timeout_ms": (_int, [_vp, _i64]),
+    "frs_exchange_status": (_int, [_vp]),
     "frs_index_search_push": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "frs_sharded_create": (_int, [_int, C.POINTER(_int), _int, _i64, _int, C.POINTER(_vp)]),
+    "frs_sharded_destroy": (_int, [_vp]),
+    "frs_sharded_n_shards": (_int, [_vp]),
+    "frs_sharded_size": (_i64, [_vp]),
+    "frs_sharded_capacity": (_i64, [_vp]),
+    "frs_sharded_block_rows": (_i64, [_vp]),
+    "frs_sharded_shard": (_vp, [_vp, _int]),
+    "frs_sharded_set_size": (_int, [_vp, _i64]),
+    "frs_sharded_add_host": (_int, [_vp, _vp, _vp, _i64]),
+    "frs_sharded_set_rows_host": (_int, [_vp, _i64, _vp, _vp, _i64]),
+    "frs_sharded_read_rows_host": (_int, [_vp, _i64, _i64, _vp]),
+    "frs_sharded_export_raw": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "frs_sharded_import_raw": (_int, [_vp, _vp, _vp, _i64]),
+    "frs_sharded_search_host": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "frs_sharded_search_host_submit": (_int, [_vp, _vp, _vp, _vp, _int, _int, C.POINTER(_int)]),
+    "frs_sharded_search_host_collect": (_int, [_vp, _int, _vp, _vp]),
     "frs_index_last_queries": (_int, [_vp, _vp, _vp]),
     "frs_index_debug_scores": (_int, [_vp, _vp, _int, _vp, _vp]),
     "frs_index_last_stats": (_int, [_vp, C.POINTER(_i64)]),
     "frs_index_set_profiling": (_int, [_vp, _int]),
     "frs_index_read_profile": (_int, [_vp, C.POINTER(C.c_double)]),
+    "frs_index_read_profile_ex": (_int, [_vp, C.POINTER(C.c_double)]),
     "frs_index_read_timeline": (_int, [_vp, _vp, _int]),
     "frs_encoder_create": (_int, [_int, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),
     "frs_encoder_destroy": (_int, [_vp]),

@@ -26,12 +26,18 @@ _DOCTYPE_LIMIT = 127
 
 
 class Collection:
-    def __init__(self, capacity: int, dtype: str = "bf16", device: int = 0, index=None):
-        """index: an object with VectorIndex's add/set_rows/set_codes/search (tests inject a CPU double)."""
+    def __init__(self, capacity: int, dtype: str = "bf16", device: int = 0, index=None, devices=None):
+        """index: an object with VectorIndex's add/set_rows/set_codes/search (tests inject a CPU double).
+        devices: a list of CUDA devices -> the rows are sharded over them behind one handle
+        (multigpu.MultiGpuIndex, one process driving all GPUs); default: one GPU (`device`)."""
+        if index is None and devices is not None and len(devices) > 1:
+            from .multigpu import MultiGpuIndex
+
+            index = MultiGpuIndex(capacity, dtype=dtype, devices=devices)
         if index is None:
             from .index import VectorIndex
 
-            index = VectorIndex(capacity, dtype=dtype, device=device)
+            index = VectorIndex(capacity, dtype=dtype, device=devices[0] if devices else device)
         self.index = index
         self.capacity = int(capacity)
         self._tickers: dict[str, int] = {}
@@ -144,23 +150,17 @@ class Collection:
             self._ticker_tiles[int(t)] = new if old is None else np.union1d(old, new)
 
     def _set_row(self, row: int, vec: np.ndarray, code: np.ndarray) -> None:
-        import torch
-
-        dev = self.index.device
-        self.index.set_rows(row, torch.from_numpy(vec).to(dev), torch.from_numpy(code.astype(np.int64)).to(torch.int32).to(dev))
+        self.index.set_rows(row, vec, code)
 
     def delete(self, ids: Sequence[Any]) -> None:
         """Tombstone the rows of these ids (they stop matching any query)."""
-        import torch
-
         with self._lock:
             for pid in ids:
                 row = self._row_of_id.pop(pid, None)
                 if row is None:
                     continue
                 self._codes[row] |= CODE_TOMBSTONE
-                c = torch.tensor([int(self._codes[row]) - (1 << 32)], dtype=torch.int64).to(torch.int32).to(self.index.device)
-                self.index.set_codes(row, c)
+                self.index.set_codes(row, self._codes[row:row + 1])
 
     # -- read path --------------------------------------------------------------------------------
     def search(self, query_vecs, ticker, limit: int = 15, document_type=None):
@@ -233,7 +233,8 @@ class Collection:
                            "tickers": self._tickers, "doctypes": self._doctypes}, f)
 
     @classmethod
-    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0, index=None, chunk_rows: int = 1 << 20):
+    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0, index=None, chunk_rows: int = 1 << 20,
+             devices=None):
         """Rebuild a collection saved by `save`; every query then returns bit-identical ids and scores."""
         import json
         import os
@@ -241,7 +242,7 @@ class Collection:
         with open(os.path.join(path, "meta.json")) as f:
             meta = json.load(f)
         n = int(meta["rows"])
-        c = cls(max(int(capacity or 0), n, 1), dtype=meta["dtype"], device=device, index=index)
+        c = cls(max(int(capacity or 0), n, 1), dtype=meta["dtype"], device=device, index=index, devices=devices)
         codes = np.load(os.path.join(path, "codes.npy"))
         esz, dt = (4, np.float32) if meta["dtype"] == "f32" else (2, np.uint16)
         with open(os.path.join(path, "rows.bin"), "rb") as f:
@@ -326,8 +327,11 @@ class _CollectionsResponse:
 class QdrantCompat:
     """Duck-typed stand-in for `QdrantClient` (main.py:92-95 get_qdrant)."""
 
-    def __init__(self, capacity: int = 1_000_000, dtype: str = "bf16", device: int = 0, index_factory=None):
+    def __init__(self, capacity: int = 1_000_000, dtype: str = "bf16", device: int = 0, index_factory=None, devices=None):
+        """devices=[0, 1, ...]: every collection is sharded over these GPUs behind the one client object, the
+        way the reference's single server process holds one QdrantClient (main2.py:104-108)."""
         self._capacity, self._dtype, self._device, self._factory = capacity, dtype, device, index_factory
+        self._devices = list(devices) if devices is not None else None
         self._collections: dict[str, Collection] = {}
 
     def collection_exists(self, collection_name: str) -> bool:
@@ -342,7 +346,8 @@ class QdrantCompat:
         if size != FRS_DIM or str(dist).lower() not in ("cosine", "distance.cosine"):
             raise ValueError("only VectorParams(size=384, distance=COSINE) collections are supported")
         idx = self._factory(self._capacity) if self._factory else None
-        self._collections[collection_name] = Collection(self._capacity, self._dtype, self._device, index=idx)
+        self._collections[collection_name] = Collection(self._capacity, self._dtype, self._device, index=idx,
+                                                        devices=self._devices)
         return True
 
     def collection(self, collection_name: str) -> Collection:

@@ -8,7 +8,11 @@
 //          sequence number in the peer's flag word.  frs_index_search_push (index.cu) does this in the TAIL OF
 //          THE LOCAL MERGE KERNEL (scan.cu merge_kernel: one CTA per query pushes its k results, the last CTA
 //          publishes the flags); frs_exchange_push is the stand-alone form for a block that already exists;
-//   wait   a one-warp kernel spins (bounded) until all `world` flags have reached the current sequence number;
+//   wait   a one-warp kernel spins until all `world` flags have reached the current sequence number.  The wait is
+//          bounded by a wall-clock time-out (default 30 s, frs_exchange_set_timeout_ms): a rank that is merely late
+//          (host stall, lazy module load, a save in progress) is waited for; a lost one poisons the batch — the
+//          merge emits an empty result and the host entry points return FRS_E_TIMEOUT — instead of trapping,
+//          which would destroy this rank's CUDA context and its resident shard;
 //   merge  the existing cross-shard merge kernel runs over the local gather buffer.
 //
 // The data crosses NVSwitch exactly once per (source, destination) pair, no kernel of a collective library has to be
@@ -29,13 +33,8 @@
 
 #include <vector>
 
-#include "../../include/frs_b200.h"
-#include "exchange.cuh"
-#include "scan.cuh"
+#include "index.cuh"
 
-namespace frs {
-int abi_set_err(int code, const char* fmt, ...);
-}
 using frs::abi_set_err;
 using frs::kExchangeSlots;
 
@@ -63,24 +62,52 @@ exchange_push_kernel(const uint64_t* __restrict__ local, uint64_t* const* __rest
   }
 }
 
-// one warp: lane r waits for rank r's flag (bounded: a lost peer must trap, not hang the GPU)
-__global__ void exchange_wait_kernel(const uint32_t* __restrict__ flags, int world, uint32_t seq) {
+// one warp: lane r waits for rank r's flag.  Bounded by wall-clock time; on time-out the batch is poisoned and
+// the sequence number reported to the host — never a trap.  A poisoned exchange stays poisoned (the ranks'
+// sequence numbers can no longer be trusted): the owner destroys and re-creates it on every rank.
+__global__ void exchange_wait_kernel(const uint32_t* __restrict__ flags, int world, uint32_t seq,
+                                     unsigned long long timeout_ns, uint32_t* poison, uint32_t* status) {
+  if (*reinterpret_cast<volatile uint32_t*>(poison) != 0u) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (int r = threadIdx.x; r < world; r += blockDim.x) {
-    uint32_t v, spins = 0;
-    do {
+    uint32_t v;
+    for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
       if ((int32_t)(v - seq) >= 0) break;
       __nanosleep(200);
-    } while (++spins < (1u << 24));  // ~ several seconds
-    if ((int32_t)(v - seq) < 0) __trap();
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) {
+        *reinterpret_cast<volatile uint32_t*>(poison) = 1u;
+        *reinterpret_cast<volatile uint32_t*>(status) = seq;
+        __threadfence_system();
+        break;
+      }
+    }
   }
+}
+
+void free_exchange(frs_exchange* ex) {
+  for (void* p : ex->opened) cudaIpcCloseMemHandle(p);
+  cudaFree(ex->gather);
+  cudaFree(ex->flags);
+  cudaFree(ex->d_peer_gather);
+  cudaFree(ex->d_peer_flags);
+  cudaFree(ex->local);
+  cudaFree(ex->counter);
+  cudaFree(ex->poison);
+  if (ex->h_status) cudaFreeHost(const_cast<uint32_t*>(ex->h_status));
+  delete ex;
 }
 
 }  // namespace
 
 extern "C" int frs_exchange_create(int device, int world, int rank, int nq_max, int k_max, frs_exchange** out) {
   if (!out) return abi_set_err(FRS_E_INVALID, "null pointer argument");
-  if (world < 1 || world > 64 || rank < 0 || rank >= world || nq_max < 1 || k_max < 1 || k_max > FRS_MAX_K)
+  *out = nullptr;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || nq_max < 1 || nq_max > FRS_MAX_BATCH || k_max < 1 ||
+      k_max > FRS_MAX_K)
     return abi_set_err(FRS_E_INVALID, "bad exchange shape (world %d rank %d nq %d k %d)", world, rank, nq_max, k_max);
   EX_TRY(cudaSetDevice(device));
   frs_exchange* ex = new frs_exchange();
@@ -89,20 +116,38 @@ extern "C" int frs_exchange_create(int device, int world, int rank, int nq_max, 
   ex->rank = rank;
   ex->nq_max = nq_max;
   ex->k_max = k_max;
-  ex->block_words = 2 * (size_t)nq_max * k_max;
+  ex->plane_words = (size_t)nq_max * k_max;
+  ex->block_words = 2 * ex->plane_words;
   const size_t gbytes = (size_t)kExchangeSlots * world * ex->block_words * 8;
+  uint32_t* hs = nullptr;
   // plain cudaMalloc (not a caching-allocator sub-block): the IPC handle names exactly this allocation
-  if (cudaMalloc(&ex->gather, gbytes) != cudaSuccess || cudaMalloc(&ex->flags, (size_t)world * 4) != cudaSuccess ||
-      cudaMalloc(&ex->d_peer_gather, (size_t)world * sizeof(void*)) != cudaSuccess ||
-      cudaMalloc(&ex->d_peer_flags, (size_t)world * sizeof(void*)) != cudaSuccess ||
-      cudaMalloc(&ex->local, ex->block_words * 8) != cudaSuccess || cudaMalloc(&ex->counter, 4) != cudaSuccess) {
-    delete ex;
-    return abi_set_err(FRS_E_CUDA, "exchange buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaError_t e = cudaMalloc(&ex->gather, gbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->flags, (size_t)world * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->d_peer_gather, (size_t)world * sizeof(void*));
+  if (e == cudaSuccess) e = cudaMalloc(&ex->d_peer_flags, (size_t)world * sizeof(void*));
+  if (e == cudaSuccess) e = cudaMalloc(&ex->local, ex->block_words * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->counter, 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->poison, 4);
+  if (e == cudaSuccess) e = cudaHostAlloc(&hs, 4, cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *hs = 0;
+    ex->h_status = hs;
+    e = cudaHostGetDevicePointer(&ex->d_status, hs, 0);
   }
-  EX_TRY(cudaMemset(ex->gather, 0, gbytes));
-  EX_TRY(cudaMemset(ex->flags, 0, (size_t)world * 4));
-  EX_TRY(cudaMemset(ex->counter, 0, 4));
-  EX_TRY(cudaDeviceSynchronize());
+  cudaFuncAttributes fa;  // load the exchange kernels now, not at their first launch (see preload_search_kernels)
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, (const void*)exchange_push_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, (const void*)exchange_wait_kernel);
+  if (e == cudaSuccess) e = frs::preload_search_kernels();
+  if (e == cudaSuccess) e = cudaMemset(ex->gather, 0, gbytes);
+  if (e == cudaSuccess) e = cudaMemset(ex->flags, 0, (size_t)world * 4);
+  if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->block_words * 8);
+  if (e == cudaSuccess) e = cudaMemset(ex->counter, 0, 4);
+  if (e == cudaSuccess) e = cudaMemset(ex->poison, 0, 4);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    free_exchange(ex);
+    return abi_set_err(FRS_E_CUDA, "exchange set-up failed: %s", cudaGetErrorString(e));
+  }
   *out = ex;
   return FRS_OK;
 }
@@ -111,15 +156,30 @@ extern "C" int frs_exchange_destroy(frs_exchange* ex) {
   if (!ex) return FRS_OK;
   cudaSetDevice(ex->device);
   cudaDeviceSynchronize();
-  for (void* p : ex->opened) cudaIpcCloseMemHandle(p);
-  cudaFree(ex->gather);
-  cudaFree(ex->flags);
-  cudaFree(ex->d_peer_gather);
-  cudaFree(ex->d_peer_flags);
-  cudaFree(ex->local);
-  cudaFree(ex->counter);
-  delete ex;
+  free_exchange(ex);
   return FRS_OK;
+}
+
+extern "C" int frs_exchange_set_timeout_ms(frs_exchange* ex, int64_t ms) {
+  if (!ex || ms < 1) return abi_set_err(FRS_E_INVALID, "bad argument");
+  ex->timeout_ns = (unsigned long long)ms * 1000000ull;
+  return FRS_OK;
+}
+
+namespace frs {
+int exchange_check(frs_exchange* ex) {
+  const uint32_t bad = ex->h_status ? *ex->h_status : 0u;
+  if (bad)
+    return abi_set_err(FRS_E_TIMEOUT,
+                       "exchange: a peer rank did not publish batch %u within %.1f s; results from that batch on are "
+                       "empty — destroy and re-create the exchange on every rank", bad, ex->timeout_ns * 1e-9);
+  return FRS_OK;
+}
+}  // namespace frs
+
+extern "C" int frs_exchange_status(frs_exchange* ex) {
+  if (!ex) return abi_set_err(FRS_E_INVALID, "null pointer argument");
+  return frs::exchange_check(ex);
 }
 
 // 128 bytes: IPC handle of the gather buffer | IPC handle of the flag array
@@ -177,36 +237,81 @@ extern "C" int frs_exchange_connect_local(frs_exchange* ex, frs_exchange* const*
   for (int r = 0; r < ex->world; ++r) {
     if (!peers[r] || peers[r]->world != ex->world || peers[r]->block_words != ex->block_words)
       return abi_set_err(FRS_E_INVALID, "peer %d does not match this exchange", r);
+    if (peers[r]->device != ex->device) {  // several GPUs of one process: map the peer's memory
+      int can = 0;
+      EX_TRY(cudaDeviceCanAccessPeer(&can, ex->device, peers[r]->device));
+      if (!can) return abi_set_err(FRS_E_CUDA, "device %d cannot access device %d", ex->device, peers[r]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return abi_set_err(FRS_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
     g[r] = peers[r]->gather;
     f[r] = peers[r]->flags;
   }
   return install_peers(ex, g, f);
 }
 
-// dev_local_packed: this rank's [2][nq][k] words (nq, k as created).  Asynchronous on `stream`.
-extern "C" int frs_exchange_push(frs_exchange* ex, const int64_t* dev_local_packed, void* stream) {
-  if (!ex || !dev_local_packed) return abi_set_err(FRS_E_INVALID, "null pointer argument");
-  if (!ex->connected) return abi_set_err(FRS_E_INVALID, "exchange is not connected");
-  EX_TRY(cudaSetDevice(ex->device));
-  ++ex->seq;
-  exchange_push_kernel<<<ex->world, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint64_t*>(dev_local_packed), ex->d_peer_gather, ex->d_peer_flags, ex->world, ex->rank,
-      (uint32_t)ex->block_words, ex->block_words, ex->seq);
+namespace frs {
+
+// The push target of this rank's NEXT batch (sequence number seq + 1).  The sequence number itself advances in
+// exchange_commit_push, after the kernel carrying the push has been enqueued successfully: a failed launch leaves
+// the ranks' sequence numbers in step.
+int exchange_begin_push(frs_exchange* ex, int nq, int k, PushTarget* t) {
+  (void)nq;
+  (void)k;
+  int rc = exchange_check(ex);
+  if (rc) return rc;
+  t->peer_gather = ex->d_peer_gather;
+  t->peer_flags = ex->d_peer_flags;
+  t->counter = ex->counter;
+  t->n_targets = ex->world;
+  t->world = ex->world;
+  t->rank = ex->rank;
+  t->seq = ex->seq + 1;
+  t->block_words = ex->block_words;
+  t->plane_words = ex->plane_words;
+  return FRS_OK;
+}
+void exchange_commit_push(frs_exchange* ex) { ++ex->seq; }
+
+// waits for every rank's push of the current sequence number, then merges [world][2][nq_max][k_max] -> [nq][k]
+int exchange_wait_merge(frs_exchange* ex, int nq, int k, float* out_s, int64_t* out_i, cudaStream_t st) {
+  exchange_wait_kernel<<<1, 64, 0, st>>>(ex->flags, ex->world, ex->seq, ex->timeout_ns, ex->poison, ex->d_status);
   EX_TRY(cudaGetLastError());
+  const uint64_t* slot = ex->gather + (size_t)(ex->seq % kExchangeSlots) * ex->world * ex->block_words;
+  EX_TRY(launch_merge_shards(reinterpret_cast<const double*>(slot), reinterpret_cast<const int64_t*>(slot) + ex->plane_words,
+                             ex->world, nq, k, ex->block_words, out_s, out_i, st, ex->poison));
   return FRS_OK;
 }
 
-// waits for every rank's push of the current sequence number, then merges [world][2][nq][k] -> [nq][k]
+}  // namespace frs
+
+// dev_local_packed: this rank's block in the exchange's layout — [2][nq_max][k_max] words, entry (q, r) of a plane at
+// q * k + r (dense [2][nq][k] when nq, k are the ones the exchange was created with).  Asynchronous on `stream`.
+extern "C" int frs_exchange_push(frs_exchange* ex, const int64_t* dev_local_packed, void* stream) {
+  if (!ex || !dev_local_packed) return abi_set_err(FRS_E_INVALID, "null pointer argument");
+  if (!ex->connected) return abi_set_err(FRS_E_INVALID, "exchange is not connected");
+  int rc = frs::exchange_check(ex);
+  if (rc) return rc;
+  EX_TRY(cudaSetDevice(ex->device));
+  exchange_push_kernel<<<ex->world, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint64_t*>(dev_local_packed), ex->d_peer_gather, ex->d_peer_flags, ex->world, ex->rank,
+      (uint32_t)ex->block_words, ex->block_words, ex->seq + 1);
+  EX_TRY(cudaGetLastError());
+  ++ex->seq;
+  return FRS_OK;
+}
+
 extern "C" int frs_exchange_wait_merge(frs_exchange* ex, float* dev_out_scores, int64_t* dev_out_ids, void* stream) {
+  return frs_exchange_wait_merge_n(ex, ex ? ex->nq_max : 0, ex ? ex->k_max : 0, dev_out_scores, dev_out_ids, stream);
+}
+
+extern "C" int frs_exchange_wait_merge_n(frs_exchange* ex, int nq, int k, float* dev_out_scores, int64_t* dev_out_ids,
+                                         void* stream) {
   if (!ex || !dev_out_scores || !dev_out_ids) return abi_set_err(FRS_E_INVALID, "null pointer argument");
   if (!ex->connected || ex->seq == 0) return abi_set_err(FRS_E_INVALID, "nothing was pushed");
+  if (nq < 1 || nq > ex->nq_max || k < 1 || k > ex->k_max) return abi_set_err(FRS_E_INVALID, "nq / k exceed the exchange's");
   EX_TRY(cudaSetDevice(ex->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  exchange_wait_kernel<<<1, 64, 0, st>>>(ex->flags, ex->world, ex->seq);
-  EX_TRY(cudaGetLastError());
-  const uint64_t* slot = ex->gather + (size_t)(ex->seq % kExchangeSlots) * ex->world * ex->block_words;
-  const size_t plane = (size_t)ex->nq_max * ex->k_max;
-  EX_TRY(frs::launch_merge_shards(reinterpret_cast<const double*>(slot), reinterpret_cast<const int64_t*>(slot) + plane,
-                                  ex->world, ex->nq_max, ex->k_max, 2 * plane, dev_out_scores, dev_out_ids, st));
-  return FRS_OK;
+  return frs::exchange_wait_merge(ex, nq, k, dev_out_scores, dev_out_ids, (cudaStream_t)stream);
 }

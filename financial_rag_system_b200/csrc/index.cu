@@ -7,12 +7,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <new>
 
-#include "../../include/frs_b200.h"
-#include "exchange.cuh"
-#include "scan.cuh"
+#include "index.cuh"
 
 using namespace frs;
 
@@ -119,87 +118,49 @@ static int make_tmap(CUtensorMap* m, void* base, bool f32, uint64_t rows, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// index object
+// index object (struct frs_index: index.cuh)
 // ---------------------------------------------------------------------------------------------
-struct frs_index {
-  int device = 0;
-  int dtype = FRS_DTYPE_BF16;
-  int64_t capacity = 0;
-  int64_t size = 0;
-  int64_t base = 0;
-  int sm_count = 0;
-  int grid_override = 0;
-  void* rows = nullptr;
-  uint32_t* codes = nullptr;
-  CUtensorMap tmap_rows, tmap_q;
-  // search workspace (device)
-  void* qop = nullptr;
-  float* qrec = nullptr;
-  uint32_t* qcode = nullptr;
-  uint32_t* qmask = nullptr;
-  uint64_t* part_keys = nullptr;
-  uint32_t* part_cnt = nullptr;
-  unsigned long long* stats = nullptr;
-  float* gmax = nullptr;
-  float* gsample = nullptr;
-  unsigned long long* timeline = nullptr;
-  int max_parts = 0;
-  // profiling (off by default): CUDA events around each kernel of a search
-  static constexpr int kProfRing = 256;
-  int prof_mode = 0;          // 0 off, 1 events, 2 events + in-kernel timeline
-  int prof_calls = 0;         // searches recorded since the last read
-  cudaEvent_t* prof_ev = nullptr;  // [kProfRing][4]: before prep, after prep, after scan, after merge
-  // staging for the *_host entry points
-  float* d_q = nullptr;
-  uint32_t* d_code = nullptr;
-  uint32_t* d_mask = nullptr;
-  float* d_out_s = nullptr;
-  int64_t* d_out_ids = nullptr;
-  float* h_q = nullptr;
-  uint32_t* h_code = nullptr;
-  uint32_t* h_mask = nullptr;
-  float* h_out_s = nullptr;
-  int64_t* h_out_ids = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that uses the workspace
-  std::mutex mu;
-  int last_grid = 0;
-  int last_launches = 0;
-  bool f32() const { return dtype == FRS_DTYPE_F32; }
-  size_t row_bytes() const { return (size_t)kDim * (f32() ? 4 : 2); }
-};
-
 static void free_index(frs_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
   cudaFree(ix->rows);
   cudaFree(ix->codes);
-  cudaFree(ix->qop);
-  cudaFree(ix->qrec);
-  cudaFree(ix->qcode);
-  cudaFree(ix->qmask);
-  cudaFree(ix->part_keys);
-  cudaFree(ix->part_cnt);
-  cudaFree(ix->stats);
-  cudaFree(ix->gmax);
-  cudaFree(ix->gsample);
+  for (SearchWs& w : ix->ws) {
+    cudaFree(w.qop);
+    cudaFree(w.qrec);
+    cudaFree(w.qcode);
+    cudaFree(w.qmask);
+    cudaFree(w.part_keys);
+    cudaFree(w.part_cnt);
+    cudaFree(w.stats);
+    cudaFree(w.gmax);
+    cudaFree(w.gsample);
+    cudaFree(w.spill);
+    if (w.free) cudaEventDestroy(w.free);
+  }
   cudaFree(ix->timeline);
+  if (ix->br_first) cudaEventDestroy(ix->br_first);
+  if (ix->br_last) cudaEventDestroy(ix->br_last);
   if (ix->prof_ev) {
-    for (int i = 0; i < frs_index::kProfRing * 4; ++i) cudaEventDestroy(ix->prof_ev[i]);
+    for (int i = 0; i < frs_index::kProfRing * kProfEvents; ++i) cudaEventDestroy(ix->prof_ev[i]);
     delete[] ix->prof_ev;
   }
-  cudaFree(ix->d_q);
-  cudaFree(ix->d_code);
-  cudaFree(ix->d_mask);
-  cudaFree(ix->d_out_s);
-  cudaFree(ix->d_out_ids);
-  cudaFreeHost(ix->h_q);
-  cudaFreeHost(ix->h_code);
-  cudaFreeHost(ix->h_mask);
-  cudaFreeHost(ix->h_out_s);
-  cudaFreeHost(ix->h_out_ids);
-  if (ix->ws_free) cudaEventDestroy(ix->ws_free);
-  if (ix->stream) cudaStreamDestroy(ix->stream);
+  for (HostSlot& h : ix->hs) {
+    cudaFree(h.d_in);
+    cudaFree(h.d_out);
+    cudaFreeHost(h.h_in);
+    cudaFreeHost(h.h_out);
+    if (h.done) cudaEventDestroy(h.done);
+  }
+  for (int i = 0; i < kJobRing; ++i) {
+    if (ix->job_in[i]) cudaEventDestroy(ix->job_in[i]);
+    if (ix->job_prep[i]) cudaEventDestroy(ix->job_prep[i]);
+    if (ix->job_scan[i]) cudaEventDestroy(ix->job_scan[i]);
+    if (ix->job_done[i]) cudaEventDestroy(ix->job_done[i]);
+  }
+  if (ix->rows_ready) cudaEventDestroy(ix->rows_ready);
+  for (cudaStream_t s : {ix->s_prep, ix->s_scan, ix->s_merge, ix->stream})
+    if (s) cudaStreamDestroy(s);
   delete ix;
 }
 
@@ -219,6 +180,7 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
                    prop.major, prop.minor);
   frs_index* ix = new (std::nothrow) frs_index();
   if (!ix) return set_err(FRS_E_INVALID, "out of host memory");
+  for (int i = 0; i < kJobRing; ++i) ix->job_in[i] = ix->job_prep[i] = ix->job_scan[i] = ix->job_done[i] = nullptr;
   ix->device = device;
   ix->dtype = dtype;
   ix->capacity = capacity;
@@ -237,36 +199,54 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
     }                                                                                      \
   } while (0)
   IX_TRY(cudaMalloc(&ix->rows, (size_t)cap_pad * ix->row_bytes()));
+  // never-written rows must not hold NaN bit patterns: a tile is read whole and 0 * NaN would poison its neighbours' sums
+  IX_TRY(cudaMemset(ix->rows, 0, (size_t)cap_pad * ix->row_bytes()));
   IX_TRY(cudaMalloc(&ix->codes, (size_t)cap_pad * 4));
   IX_TRY(cudaMemset(ix->codes, 0xFF, (size_t)cap_pad * 4));
-  IX_TRY(cudaMalloc(&ix->qop, (size_t)kNQ * ix->row_bytes()));
-  IX_TRY(cudaMalloc(&ix->qrec, (size_t)kNQ * kDim * 4));
-  IX_TRY(cudaMemset(ix->qrec, 0, (size_t)kNQ * kDim * 4));
-  IX_TRY(cudaMalloc(&ix->qcode, kNQ * 4));
-  IX_TRY(cudaMalloc(&ix->qmask, kNQ * 4));
-  IX_TRY(cudaMalloc(&ix->part_keys, (size_t)ix->max_parts * kNQ * kListCap * 8));
-  IX_TRY(cudaMalloc(&ix->part_cnt, (size_t)ix->max_parts * kNQ * 4));
-  IX_TRY(cudaMalloc(&ix->stats, kStatSlots * 8));
-  IX_TRY(cudaMemset(ix->stats, 0, kStatSlots * 8));
-  IX_TRY(cudaMalloc(&ix->gmax, (size_t)kNQ * kGmaxPad * 4));
-  IX_TRY(cudaMalloc(&ix->gsample, (size_t)kNQ * kSampleBlocks * 4));
+  for (SearchWs& w : ix->ws) {
+    IX_TRY(cudaMalloc(&w.qop, (size_t)kNQ * ix->row_bytes()));
+    IX_TRY(cudaMalloc(&w.qrec, (size_t)kNQ * kDim * 4));
+    IX_TRY(cudaMemset(w.qrec, 0, (size_t)kNQ * kDim * 4));
+    IX_TRY(cudaMalloc(&w.qcode, kNQ * 4));
+    IX_TRY(cudaMalloc(&w.qmask, kNQ * 4));
+    IX_TRY(cudaMalloc(&w.part_keys, (size_t)ix->max_parts * kNQ * kListCap * 8));
+    IX_TRY(cudaMalloc(&w.part_cnt, (size_t)ix->max_parts * kNQ * 4));
+    IX_TRY(cudaMalloc(&w.stats, kStatSlots * 8));
+    IX_TRY(cudaMemset(w.stats, 0, kStatSlots * 8));
+    IX_TRY(cudaMalloc(&w.gmax, (size_t)kNQ * kGmaxPad * 4));
+    IX_TRY(cudaMalloc(&w.gsample, (size_t)kNQ * kSampleBlocks * 4));
+    IX_TRY(cudaMalloc(&w.spill, merge_spill_bytes()));
+    IX_TRY(cudaEventCreateWithFlags(&w.free, cudaEventDisableTiming));
+  }
   IX_TRY(cudaMalloc(&ix->timeline, (size_t)kGmaxPad * 16 * 8));
   IX_TRY(cudaMemset(ix->timeline, 0, (size_t)kGmaxPad * 16 * 8));
-  IX_TRY(cudaMalloc(&ix->d_q, (size_t)kNQ * kDim * 4));
-  IX_TRY(cudaMalloc(&ix->d_code, kNQ * 4));
-  IX_TRY(cudaMalloc(&ix->d_mask, kNQ * 4));
-  IX_TRY(cudaMalloc(&ix->d_out_s, (size_t)kNQ * kMaxK * 4));
-  IX_TRY(cudaMalloc(&ix->d_out_ids, (size_t)kNQ * kMaxK * 8));
-  IX_TRY(cudaMallocHost(&ix->h_q, (size_t)kNQ * kDim * 4));
-  IX_TRY(cudaMallocHost(&ix->h_code, kNQ * 4));
-  IX_TRY(cudaMallocHost(&ix->h_mask, kNQ * 4));
-  IX_TRY(cudaMallocHost(&ix->h_out_s, (size_t)kNQ * kMaxK * 4));
-  IX_TRY(cudaMallocHost(&ix->h_out_ids, (size_t)kNQ * kMaxK * 8));
+  for (HostSlot& h : ix->hs) {
+    IX_TRY(cudaMalloc(&h.d_in, kHostInBytes));
+    IX_TRY(cudaMalloc(&h.d_out, kHostOutBytes));
+    IX_TRY(cudaMallocHost(&h.h_in, kHostInBytes));
+    IX_TRY(cudaMallocHost(&h.h_out, kHostOutBytes));
+    IX_TRY(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+  }
+  for (int i = 0; i < kJobRing; ++i) {
+    IX_TRY(cudaEventCreateWithFlags(&ix->job_in[i], cudaEventDisableTiming));
+    IX_TRY(cudaEventCreateWithFlags(&ix->job_prep[i], cudaEventDisableTiming));
+    IX_TRY(cudaEventCreateWithFlags(&ix->job_scan[i], cudaEventDisableTiming));
+    IX_TRY(cudaEventCreateWithFlags(&ix->job_done[i], cudaEventDisableTiming));
+  }
+  IX_TRY(cudaEventCreateWithFlags(&ix->rows_ready, cudaEventDisableTiming));
+  // the scan stream outranks the others: when a scan and a prep / merge are both ready, the scan's CTAs go first
+  int prio_lo = 0, prio_hi = 0;
+  IX_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_prep, cudaStreamNonBlocking, prio_lo));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_scan, cudaStreamNonBlocking, prio_hi));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_merge, cudaStreamNonBlocking, prio_lo));
   IX_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-  IX_TRY(cudaEventCreateWithFlags(&ix->ws_free, cudaEventDisableTiming));
+  IX_TRY(preload_search_kernels());
+  IX_TRY(cudaDeviceSynchronize());  // the memsets above ran on the legacy stream; the internal streams do not sync with it
 #undef IX_TRY
   int rc = make_tmap(&ix->tmap_rows, ix->rows, f32, (uint64_t)cap_pad, kTileM);
-  if (!rc) rc = make_tmap(&ix->tmap_q, ix->qop, f32, kNQ, kNQ);
+  for (SearchWs& w : ix->ws)
+    if (!rc) rc = make_tmap(&w.tmap_q, w.qop, f32, kNQ, kNQ);
   if (rc) {
     free_index(ix);
     return rc;
@@ -286,6 +266,7 @@ extern "C" int frs_index_destroy(frs_index* idx) {
 extern "C" int64_t frs_index_size(const frs_index* idx) { return idx ? idx->size : 0; }
 extern "C" int64_t frs_index_capacity(const frs_index* idx) { return idx ? idx->capacity : 0; }
 extern "C" int frs_index_dtype(const frs_index* idx) { return idx ? idx->dtype : FRS_E_INVALID; }
+extern "C" int frs_index_device(const frs_index* idx) { return idx ? idx->device : FRS_E_INVALID; }
 extern "C" int frs_index_set_base(frs_index* idx, int64_t base) {
   if (!idx) return set_err(FRS_E_INVALID, "idx is null");
   idx->base = base;
@@ -296,10 +277,19 @@ extern "C" int frs_index_set_scan_grid(frs_index* idx, int grid) {
   idx->grid_override = grid;
   return FRS_OK;
 }
+// The scan kernel is persistent with one CTA per SM and nearly all of an SM's shared memory, so nothing else fits
+// next to one of its CTAs.  The pipelined entry points therefore run it on (SMs - reserve) CTAs: the prep kernel of
+// the next batch and the merge / exchange kernels of the previous one run on the SMs left over.
+extern "C" int frs_index_set_pipeline_reserve(frs_index* idx, int sms) {
+  if (!idx || sms < 0 || sms > 64) return set_err(FRS_E_INVALID, "bad argument");
+  idx->pipe_reserve = sms;
+  return FRS_OK;
+}
 extern "C" void* frs_index_rows_ptr(frs_index* idx) { return idx ? idx->rows : nullptr; }
 extern "C" uint32_t* frs_index_codes_ptr(frs_index* idx) { return idx ? idx->codes : nullptr; }
 extern "C" int frs_index_set_size(frs_index* idx, int64_t n) {
   if (!idx || n < 0 || n > idx->capacity) return set_err(FRS_E_INVALID, "size out of range");
+  std::lock_guard<std::mutex> lk(idx->mu);
   idx->size = n;
   return FRS_OK;
 }
@@ -307,77 +297,108 @@ extern "C" int frs_index_set_size(frs_index* idx, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // write path
 // ---------------------------------------------------------------------------------------------
+// Ordering of writes against searches (the reference serves queries from up to 25 threads while ingest.py is
+// upserting, main2.py:52-53): a write kernel is chained behind the previous write (`rows_ready`) and re-records
+// that event; every search waits on it before its first kernel, so a search whose size snapshot includes new
+// rows never reads them half-written.  An in-place overwrite additionally waits for the searches in flight.
+static int write_begin(frs_index* ix, cudaStream_t st, bool in_place) {
+  CU_TRY(cudaStreamWaitEvent(st, ix->rows_ready, 0));
+  if (in_place)
+    for (SearchWs& w : ix->ws) CU_TRY(cudaStreamWaitEvent(st, w.free, 0));
+  return FRS_OK;
+}
+
 extern "C" int frs_index_set_rows(frs_index* idx, int64_t row0, const float* dev_vecs,
                                   const uint32_t* dev_codes, int64_t n, void* stream) {
   if (!idx || n < 0 || row0 < 0 || (n > 0 && !dev_vecs)) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
   if (row0 + n > idx->size) return set_err(FRS_E_INVALID, "rows [%lld,%lld) beyond size %lld", (long long)row0,
                                            (long long)(row0 + n), (long long)idx->size);
-  CU_TRY(cudaSetDevice(idx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = write_begin(idx, st, true);
+  if (rc) return rc;
+  // dev_codes == null keeps the stored payload codes
   CU_TRY(launch_store_rows(idx->f32(), dev_vecs, dev_codes, n,
-                           (char*)idx->rows + (size_t)row0 * idx->row_bytes(), idx->codes + row0,
-                           (cudaStream_t)stream));
+                           (char*)idx->rows + (size_t)row0 * idx->row_bytes(), dev_codes ? idx->codes + row0 : nullptr, st));
+  CU_TRY(cudaEventRecord(idx->rows_ready, st));
   return FRS_OK;
 }
 
 extern "C" int frs_index_add(frs_index* idx, const float* dev_vecs, const uint32_t* dev_codes, int64_t n,
                              void* stream) {
   if (!idx || n < 0 || (n > 0 && !dev_vecs)) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
   std::lock_guard<std::mutex> lk(idx->mu);
   if (idx->size + n > idx->capacity)
     return set_err(FRS_E_CAPACITY, "index full: size %lld + %lld > capacity %lld", (long long)idx->size,
                    (long long)n, (long long)idx->capacity);
-  CU_TRY(cudaSetDevice(idx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = write_begin(idx, st, false);
+  if (rc) return rc;
   CU_TRY(launch_store_rows(idx->f32(), dev_vecs, dev_codes, n,
                            (char*)idx->rows + (size_t)idx->size * idx->row_bytes(),
-                           idx->codes + idx->size, (cudaStream_t)stream));
-  idx->size += n;
+                           idx->codes + idx->size, st));
+  CU_TRY(cudaEventRecord(idx->rows_ready, st));
+  idx->size += n;  // published under the lock; searches wait on rows_ready before reading the new rows
   return FRS_OK;
 }
 
 extern "C" int frs_index_add_host(frs_index* idx, const float* host_vecs, const uint32_t* host_codes,
                                   int64_t n) {
   if (!idx || n < 0 || (n > 0 && !host_vecs)) return set_err(FRS_E_INVALID, "bad argument");
-  if (idx->size + n > idx->capacity)
-    return set_err(FRS_E_CAPACITY, "index full: size %lld + %lld > capacity %lld", (long long)idx->size,
-                   (long long)n, (long long)idx->capacity);
   CU_TRY(cudaSetDevice(idx->device));
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);  // early verdict; frs_index_add re-checks under the same lock
+    if (idx->size + n > idx->capacity)
+      return set_err(FRS_E_CAPACITY, "index full: size %lld + %lld > capacity %lld", (long long)idx->size,
+                     (long long)n, (long long)idx->capacity);
+  }
   const int64_t chunk = 16384;
   float* d_v = nullptr;
   uint32_t* d_c = nullptr;
-  CU_TRY(cudaMalloc(&d_v, (size_t)chunk * kDim * 4));
-  cudaError_t e = cudaMalloc(&d_c, (size_t)chunk * 4);
+  cudaStream_t st = nullptr;  // a stream of this call: concurrent add_host callers do not share staging
+  CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaError_t e = cudaMalloc(&d_v, (size_t)chunk * kDim * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_c, (size_t)chunk * 4);
   if (e != cudaSuccess) {
     cudaFree(d_v);
+    cudaStreamDestroy(st);
     return set_err(FRS_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
   }
   int rc = FRS_OK;
   for (int64_t o = 0; o < n && rc == FRS_OK; o += chunk) {
     const int64_t m = n - o < chunk ? n - o : chunk;
-    e = cudaMemcpyAsync(d_v, host_vecs + o * kDim, (size_t)m * kDim * 4, cudaMemcpyHostToDevice, idx->stream);
+    e = cudaMemcpyAsync(d_v, host_vecs + o * kDim, (size_t)m * kDim * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && host_codes)
-      e = cudaMemcpyAsync(d_c, host_codes + o, (size_t)m * 4, cudaMemcpyHostToDevice, idx->stream);
+      e = cudaMemcpyAsync(d_c, host_codes + o, (size_t)m * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) {
       rc = set_err(FRS_E_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
       break;
     }
-    rc = frs_index_add(idx, d_v, host_codes ? d_c : nullptr, m, idx->stream);
+    rc = frs_index_add(idx, d_v, host_codes ? d_c : nullptr, m, st);
     if (rc == FRS_OK) {
-      e = cudaStreamSynchronize(idx->stream);
+      e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) rc = set_err(FRS_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
     }
   }
   cudaFree(d_v);
   cudaFree(d_c);
+  cudaStreamDestroy(st);
   return rc;
 }
 
 extern "C" int frs_index_set_codes(frs_index* idx, int64_t row0, const uint32_t* dev_codes, int64_t n,
                                    void* stream) {
-  if (!idx || n < 0 || row0 < 0 || row0 + n > idx->size || (n > 0 && !dev_codes))
-    return set_err(FRS_E_INVALID, "bad argument");
+  if (!idx || n < 0 || row0 < 0 || (n > 0 && !dev_codes)) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
-  CU_TRY(cudaMemcpyAsync(idx->codes + row0, dev_codes, (size_t)n * 4, cudaMemcpyDeviceToDevice,
-                         (cudaStream_t)stream));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (row0 + n > idx->size) return set_err(FRS_E_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = write_begin(idx, st, true);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(idx->codes + row0, dev_codes, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(cudaEventRecord(idx->rows_ready, st));
   return FRS_OK;
 }
 
@@ -385,6 +406,7 @@ extern "C" int frs_index_read_rows(frs_index* idx, int64_t row0, int64_t n, floa
   if (!idx || n < 0 || row0 < 0 || row0 + n > idx->size || (n > 0 && !dev_out))
     return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
+  CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, idx->rows_ready, 0));
   CU_TRY(launch_read_rows(idx->f32(), (const char*)idx->rows + (size_t)row0 * idx->row_bytes(), n, dev_out,
                           (cudaStream_t)stream));
   return FRS_OK;
@@ -416,7 +438,7 @@ extern "C" int frs_index_export_raw(frs_index* idx, int64_t row0, int64_t n, voi
   if (n == 0) return FRS_OK;
   CU_TRY(cudaSetDevice(idx->device));
   std::lock_guard<std::mutex> lk(idx->mu);
-  CU_TRY(cudaStreamSynchronize(idx->stream));
+  CU_TRY(cudaEventSynchronize(idx->rows_ready));
   CU_TRY(cudaMemcpy(host_rows, (const char*)idx->rows + (size_t)row0 * idx->row_bytes(), (size_t)n * idx->row_bytes(),
                     cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(host_codes, idx->codes + row0, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -425,12 +447,12 @@ extern "C" int frs_index_export_raw(frs_index* idx, int64_t row0, int64_t n, voi
 
 extern "C" int frs_index_import_raw(frs_index* idx, const void* host_rows, const uint32_t* host_codes, int64_t n) {
   if (!idx || n < 0 || (n > 0 && (!host_rows || !host_codes))) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
   std::lock_guard<std::mutex> lk(idx->mu);
   if (idx->size + n > idx->capacity)
     return set_err(FRS_E_CAPACITY, "index full: size %lld + %lld > capacity %lld", (long long)idx->size, (long long)n,
                    (long long)idx->capacity);
   if (n == 0) return FRS_OK;
-  CU_TRY(cudaSetDevice(idx->device));
   CU_TRY(cudaMemcpy((char*)idx->rows + (size_t)idx->size * idx->row_bytes(), host_rows, (size_t)n * idx->row_bytes(),
                     cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(idx->codes + idx->size, host_codes, (size_t)n * 4, cudaMemcpyHostToDevice));
@@ -441,47 +463,56 @@ extern "C" int frs_index_import_raw(frs_index* idx, const void* host_rows, const
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
-static int scan_grid(const frs_index* ix, uint32_t num_tiles) {
-  int g = ix->grid_override > 0 ? ix->grid_override : ix->sm_count;
+static int scan_grid(const frs_index* ix, uint32_t num_tiles, int reserve = 0) {
+  int g = ix->grid_override > 0 ? ix->grid_override : ix->sm_count - (ix->sm_count > 4 * reserve ? reserve : 0);
   if (g > ix->max_parts) g = ix->max_parts;
   if ((uint32_t)g > num_tiles) g = (int)num_tiles;
   return g;
 }
 
-// prep -> scan -> merge on `st`.  Exactly one of (out_s32) / (out_s64) may be null.
-static int search_impl(frs_index* ix, const float* q, const uint32_t* code, const uint32_t* mask, int nq,
-                       int k, float* out_s32, double* out_s64, int64_t* out_ids, cudaStream_t st,
-                       const uint32_t* tile_ids = nullptr, int64_t n_tile_ids = 0, frs_exchange* push = nullptr) {
-  if (!ix) return set_err(FRS_E_INVALID, "idx is null");
-  if (nq < 1 || nq > kNQ) return set_err(FRS_E_INVALID, "nq must be in [1,%d] (got %d)", kNQ, nq);
-  if (k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "k must be in [1,%d] (got %d)", kMaxK, k);
-  if (!q || !code || !mask || !out_ids || (!out_s32 && !out_s64)) return set_err(FRS_E_INVALID, "null pointer argument");
-  CU_TRY(cudaSetDevice(ix->device));
-  std::lock_guard<std::mutex> lk(ix->mu);
+namespace frs {
+
+// prep -> scan -> merge.  Caller holds ix->mu and has selected the device.  Exactly one of out_s32 / out_s64 may be null.
+int search_enqueue(frs_index* ix, const SearchArgs& a, const SearchLaunch& L) {
+  if (a.nq < 1 || a.nq > kNQ) return set_err(FRS_E_INVALID, "nq must be in [1,%d] (got %d)", kNQ, a.nq);
+  if (a.k < 1 || a.k > kMaxK) return set_err(FRS_E_INVALID, "k must be in [1,%d] (got %d)", kMaxK, a.k);
+  if (!a.q || !a.code || !a.mask || !a.out_ids || (!a.out_s32 && !a.out_s64))
+    return set_err(FRS_E_INVALID, "null pointer argument");
   const bool f32 = ix->f32();
   const float eps = f32 ? kEpsTF32 : kEpsBF16;
-  // the workspace is shared by all calls on this index: order this call after the previous one
-  CU_TRY(cudaStreamWaitEvent(st, ix->ws_free, 0));
+  SearchWs& w = ix->ws[ix->ws_next];
+  ix->ws_last = ix->ws_next;
+  ix->ws_next = (ix->ws_next + 1) % kWsRing;
+  cudaEvent_t* pev = ix->prof_mode == 3 ? nullptr : L.prof;
+  const bool bracket = ix->prof_mode == 3 && ix->br_first;
+  // the workspace's previous search (kWsRing calls ago) and the pending writes come first
+  CU_TRY(cudaStreamWaitEvent(L.prep, w.free, 0));
+  CU_TRY(cudaStreamWaitEvent(L.prep, ix->rows_ready, 0));
   int launches = 0;
-  cudaEvent_t* pev = nullptr;
-  if (ix->prof_mode && ix->prof_ev) pev = ix->prof_ev + (size_t)(ix->prof_calls % frs_index::kProfRing) * 4;
-  if (pev) CU_TRY(cudaEventRecord(pev[0], st));
-  CU_TRY(launch_prep_queries(f32, q, code, mask, nq, ix->qop, ix->qrec, ix->qcode, ix->qmask, ix->stats, ix->gmax,
-                             ix->gsample, ix->rows, ix->codes, (uint32_t)ix->size, st));
+  if (pev) CU_TRY(cudaEventRecord(pev[0], L.prep));
+  CU_TRY(launch_prep_queries(f32, a.q, a.code, a.mask, a.nq, w.qop, w.qrec, w.qcode, w.qmask, w.stats, w.gmax,
+                             w.gsample, ix->rows, ix->codes, (uint32_t)ix->size, L.prep));
   launches++;
-  if (pev) CU_TRY(cudaEventRecord(pev[1], st));
+  if (pev) CU_TRY(cudaEventRecord(pev[1], L.prep));
+  if (L.scan != L.prep) {
+    CU_TRY(cudaEventRecord(L.ev_prep, L.prep));
+    CU_TRY(cudaStreamWaitEvent(L.scan, L.ev_prep, 0));
+  }
   const uint32_t n = (uint32_t)ix->size;
   uint32_t num_tiles = (n + kTileM - 1) / kTileM;
   // restricted scan: only the listed tiles (the caller guarantees that every row matching any query's
   // predicate lies in one of them).  A list too long for the per-CTA table falls back to the full scan.
+  const uint32_t* tile_ids = a.tile_ids;
   if (tile_ids) {
-    const int g = scan_grid(ix, (uint32_t)n_tile_ids);
-    if (n_tile_ids >= 0 && n_tile_ids <= (int64_t)num_tiles && (g == 0 || (n_tile_ids + g - 1) / g <= kMaxTileSlots))
-      num_tiles = (uint32_t)n_tile_ids;
+    const int g = scan_grid(ix, (uint32_t)a.n_tile_ids, L.reserve_sms);
+    if (a.n_tile_ids >= 0 && a.n_tile_ids <= (int64_t)num_tiles && (g == 0 || (a.n_tile_ids + g - 1) / g <= kMaxTileSlots))
+      num_tiles = (uint32_t)a.n_tile_ids;
     else
       tile_ids = nullptr;
   }
-  const int grid = scan_grid(ix, num_tiles);
+  const int grid = scan_grid(ix, num_tiles, L.reserve_sms);
+  if (pev) CU_TRY(cudaEventRecord(pev[2], L.scan));
+  if (bracket && ix->br_count == 0) CU_TRY(cudaEventRecord(ix->br_first, L.scan));
   if (grid > 0) {
     ScanParams sp{};
     sp.rows = ix->rows;
@@ -489,130 +520,373 @@ static int search_impl(frs_index* ix, const float* q, const uint32_t* code, cons
     sp.n = n;
     sp.num_tiles = num_tiles;
     sp.tile_ids = tile_ids;
-    sp.qrec = ix->qrec;
-    sp.qcode = ix->qcode;
-    sp.qmask = ix->qmask;
-    sp.nq = nq;
-    sp.k = k;
+    sp.qrec = w.qrec;
+    sp.qcode = w.qcode;
+    sp.qmask = w.qmask;
+    sp.nq = a.nq;
+    sp.k = a.k;
     sp.eps = eps;
-    sp.part_keys = ix->part_keys;
-    sp.part_cnt = ix->part_cnt;
+    sp.part_keys = w.part_keys;
+    sp.part_cnt = w.part_cnt;
     sp.dbg_scores = nullptr;
-    sp.gmax = ix->gmax;
-    sp.gsample = ix->gsample;
-    sp.stats = ix->stats;
+    sp.gmax = w.gmax;
+    sp.gsample = w.gsample;
+    sp.stats = w.stats;
     sp.timeline = ix->prof_mode == 2 ? ix->timeline : nullptr;
-    if (sp.timeline) CU_TRY(cudaMemsetAsync(ix->timeline, 0, (size_t)kGmaxPad * 16 * 8, st));
-    CU_TRY(launch_scan(f32, false, grid, ix->tmap_rows, ix->tmap_q, sp, st));
+    if (sp.timeline) CU_TRY(cudaMemsetAsync(ix->timeline, 0, (size_t)kGmaxPad * 16 * 8, L.scan));
+    CU_TRY(launch_scan(f32, false, grid, ix->tmap_rows, w.tmap_q, sp, L.scan));
     launches++;
   }
-  if (pev) CU_TRY(cudaEventRecord(pev[2], st));
+  if (pev) CU_TRY(cudaEventRecord(pev[3], L.scan));
+  if (bracket) {
+    CU_TRY(cudaEventRecord(ix->br_last, L.scan));
+    ix->br_count++;
+  }
+  if (L.merge != L.scan) {
+    CU_TRY(cudaEventRecord(L.ev_scan, L.scan));
+    CU_TRY(cudaStreamWaitEvent(L.merge, L.ev_scan, 0));
+  }
   MergeParams mp{};
-  mp.part_keys = ix->part_keys;
-  mp.part_cnt = ix->part_cnt;
-  mp.gmax = ix->gmax;
+  mp.part_keys = w.part_keys;
+  mp.part_cnt = w.part_cnt;
+  mp.gmax = w.gmax;
   mp.nparts = grid;
   mp.rows = ix->rows;
-  mp.qrec = ix->qrec;
-  mp.nq = nq;
-  mp.k = k;
+  mp.qrec = w.qrec;
+  mp.nq = a.nq;
+  mp.k = a.k;
   mp.eps = eps;
   mp.base = ix->base;
-  mp.out_s64 = out_s64;
-  mp.out_s32 = out_s32;
-  mp.out_ids = out_ids;
-  mp.stats = ix->stats;
-  if (push) {  // the exchange step rides in the tail of the merge kernel
-    ++push->seq;
-    mp.push.peer_gather = push->d_peer_gather;
-    mp.push.peer_flags = push->d_peer_flags;
-    mp.push.counter = push->counter;
-    mp.push.world = push->world;
-    mp.push.rank = push->rank;
-    mp.push.seq = push->seq;
-    mp.push.block_words = push->block_words;
-    mp.push.nq_stride = push->nq_max;
-  }
-  CU_TRY(launch_merge(f32, mp, st));
+  mp.id_block = ix->id_block;
+  mp.id_shards = ix->id_shards;
+  mp.id_shard = ix->id_shard;
+  mp.out_s64 = a.out_s64;
+  mp.out_s32 = a.out_s32;
+  mp.out_ids = a.out_ids;
+  mp.stats = w.stats;
+  mp.spill = w.spill;
+  if (a.push) mp.push = *a.push;  // the exchange step rides in the tail of the merge kernel
+  if (pev) CU_TRY(cudaEventRecord(pev[4], L.merge));
+  CU_TRY(launch_merge(f32, mp, L.merge));
   launches++;
-  if (pev) {
-    CU_TRY(cudaEventRecord(pev[3], st));
-    ix->prof_calls++;
-  }
-  CU_TRY(cudaEventRecord(ix->ws_free, st));
+  if (pev) CU_TRY(cudaEventRecord(pev[5], L.merge));
+  CU_TRY(cudaEventRecord(w.free, L.merge));
   ix->last_grid = grid;
   ix->last_launches = launches;
   return FRS_OK;
+}
+
+static cudaEvent_t* prof_slot(frs_index* ix) {
+  if (!ix->prof_mode || ix->prof_mode == 3 || !ix->prof_ev) return nullptr;
+  return ix->prof_ev + (size_t)(ix->prof_calls % frs_index::kProfRing) * kProfEvents;
+}
+
+int pipelined_begin(frs_index* ix, bool has_in, cudaStream_t in_stream, int* slot, SearchLaunch* L) {
+  const int s = (int)(ix->jobs++ % kJobRing);
+  if (has_in) {
+    CU_TRY(cudaEventRecord(ix->job_in[s], in_stream));
+    CU_TRY(cudaStreamWaitEvent(ix->s_prep, ix->job_in[s], 0));
+  }
+  L->prep = ix->s_prep;
+  L->scan = ix->s_scan;
+  L->merge = ix->s_merge;
+  L->ev_prep = ix->job_prep[s];
+  L->ev_scan = ix->job_scan[s];
+  L->prof = prof_slot(ix);
+  L->reserve_sms = ix->pipe_reserve;
+  *slot = s;
+  return FRS_OK;
+}
+
+int host_slot_acquire(frs_index* ix, int* slot) {
+  std::unique_lock<std::mutex> lk(ix->hs_mu);
+  int found = -1;
+  const bool ok = ix->hs_cv.wait_for(lk, std::chrono::seconds(30), [&] {
+    for (int i = 0; i < kHostSlots; ++i)
+      if (!ix->hs[i].busy) {
+        found = i;
+        return true;
+      }
+    return false;
+  });
+  if (!ok) return set_err(FRS_E_STATE, "all %d host-call slots of this index stayed busy for 30 s "
+                          "(more than %d submits without a collect?)", kHostSlots, kHostSlots);
+  ix->hs[found].busy = true;
+  *slot = found;
+  return FRS_OK;
+}
+
+void host_slot_release(frs_index* ix, int slot) {
+  {
+    std::lock_guard<std::mutex> lk(ix->hs_mu);
+    ix->hs[slot].busy = false;
+  }
+  ix->hs_cv.notify_one();
+}
+
+// exchange.cu
+int exchange_begin_push(frs_exchange* ex, int nq, int k, PushTarget* t);
+void exchange_commit_push(frs_exchange* ex);
+int exchange_wait_merge(frs_exchange* ex, int nq, int k, float* out_s, int64_t* out_i, cudaStream_t st);
+int exchange_check(frs_exchange* ex);
+
+}  // namespace frs
+
+static SearchLaunch in_stream_launch(frs_index* ix, cudaStream_t st) {
+  SearchLaunch L{};
+  L.prep = L.scan = L.merge = st;
+  L.prof = prof_slot(ix);
+  return L;
+}
+
+static int search_in_stream(frs_index* ix, const SearchArgs& a, cudaStream_t st) {
+  if (!ix) return set_err(FRS_E_INVALID, "idx is null");
+  CU_TRY(cudaSetDevice(ix->device));
+  std::lock_guard<std::mutex> lk(ix->mu);
+  SearchLaunch L = in_stream_launch(ix, st);
+  int rc = search_enqueue(ix, a, L);
+  if (rc == FRS_OK && L.prof) {
+    CU_TRY(cudaEventRecord(L.prof[6], st));
+    ix->prof_calls++;
+  }
+  return rc;
 }
 
 extern "C" int frs_index_search(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
                                 const uint32_t* dev_q_mask, int nq, int k, float* dev_out_scores,
                                 int64_t* dev_out_ids, void* stream) {
   if (!dev_out_scores) return set_err(FRS_E_INVALID, "null pointer argument");
-  return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, dev_out_scores, nullptr, dev_out_ids,
-                     (cudaStream_t)stream);
+  SearchArgs a;
+  a.q = dev_queries; a.code = dev_q_code; a.mask = dev_q_mask; a.nq = nq; a.k = k;
+  a.out_s32 = dev_out_scores; a.out_ids = dev_out_ids;
+  return search_in_stream(idx, a, (cudaStream_t)stream);
 }
 
 extern "C" int frs_index_search_tiles(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
                                       const uint32_t* dev_q_mask, int nq, int k, const uint32_t* dev_tile_ids,
                                       int64_t n_tiles, float* dev_out_scores, int64_t* dev_out_ids, void* stream) {
-  if (!dev_out_scores || n_tiles < 0 || (n_tiles > 0 && !dev_tile_ids)) return set_err(FRS_E_INVALID, "bad argument");
-  static uint32_t* dummy = nullptr;  // an empty list is still a restricted scan (nothing can match)
-  if (n_tiles == 0 && !dummy) CU_TRY(cudaMalloc(&dummy, 4));
-  return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, dev_out_scores, nullptr, dev_out_ids,
-                     (cudaStream_t)stream, n_tiles ? dev_tile_ids : dummy, n_tiles);
+  if (!idx || !dev_out_scores || n_tiles < 0 || (n_tiles > 0 && !dev_tile_ids)) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  // an empty list is still a restricted scan (nothing can match): any non-null pointer selects it
+  SearchArgs a;
+  a.q = dev_queries; a.code = dev_q_code; a.mask = dev_q_mask; a.nq = nq; a.k = k;
+  a.out_s32 = dev_out_scores; a.out_ids = dev_out_ids;
+  a.tile_ids = n_tiles ? dev_tile_ids : idx->codes;
+  a.n_tile_ids = n_tiles;
+  return search_in_stream(idx, a, (cudaStream_t)stream);
 }
 
 extern "C" int frs_index_search_local(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
                                       const uint32_t* dev_q_mask, int nq, int k, double* dev_out_scores64,
                                       int64_t* dev_out_ids, void* stream) {
   if (!dev_out_scores64) return set_err(FRS_E_INVALID, "null pointer argument");
-  return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, nullptr, dev_out_scores64, dev_out_ids,
-                     (cudaStream_t)stream);
+  SearchArgs a;
+  a.q = dev_queries; a.code = dev_q_code; a.mask = dev_q_mask; a.nq = nq; a.k = k;
+  a.out_s64 = dev_out_scores64; a.out_ids = dev_out_ids;
+  return search_in_stream(idx, a, (cudaStream_t)stream);
+}
+
+static int check_exchange_args(const frs_index* idx, const frs_exchange* ex, int nq, int k) {
+  if (!idx || !ex) return set_err(FRS_E_INVALID, "null pointer argument");
+  if (!ex->connected) return set_err(FRS_E_INVALID, "exchange is not connected");
+  if (nq < 1 || nq > ex->nq_max || k < 1 || k > ex->k_max)
+    return set_err(FRS_E_INVALID, "nq / k (%d / %d) exceed the exchange's (%d / %d)", nq, k, ex->nq_max, ex->k_max);
+  if (idx->device != ex->device) return set_err(FRS_E_INVALID, "index and exchange live on different devices");
+  return FRS_OK;
 }
 
 // Local pass of the sharded search WITH the exchange push fused into the merge kernel: the shard's exact top-k
 // goes into the exchange's local block and, from the same kernel, into every peer's gather buffer.  Follow with
-// frs_exchange_wait_merge.  nq and k must be the ones the exchange was created with.
+// frs_exchange_wait_merge.  nq <= nq_max and k <= k_max of the exchange; every rank passes the same nq and k.
 extern "C" int frs_index_search_push(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
                                      const uint32_t* dev_q_mask, int nq, int k, frs_exchange* ex, void* stream) {
-  if (!ex) return set_err(FRS_E_INVALID, "null pointer argument");
-  if (!ex->connected) return set_err(FRS_E_INVALID, "exchange is not connected");
-  if (nq != ex->nq_max || k != ex->k_max)
-    return set_err(FRS_E_INVALID, "nq / k (%d / %d) differ from the exchange's (%d / %d)", nq, k, ex->nq_max, ex->k_max);
-  if (idx && idx->device != ex->device) return set_err(FRS_E_INVALID, "index and exchange live on different devices");
-  const size_t plane = (size_t)nq * k;
-  return search_impl(idx, dev_queries, dev_q_code, dev_q_mask, nq, k, nullptr, reinterpret_cast<double*>(ex->local),
-                     reinterpret_cast<int64_t*>(ex->local) + plane, (cudaStream_t)stream, nullptr, 0, ex);
+  int rc = check_exchange_args(idx, ex, nq, k);
+  if (rc) return rc;
+  PushTarget t{};
+  rc = exchange_begin_push(ex, nq, k, &t);
+  if (rc) return rc;
+  SearchArgs a;
+  a.q = dev_queries; a.code = dev_q_code; a.mask = dev_q_mask; a.nq = nq; a.k = k;
+  a.out_s64 = reinterpret_cast<double*>(ex->local);
+  a.out_ids = reinterpret_cast<int64_t*>(ex->local) + ex->plane_words;
+  a.push = &t;
+  rc = search_in_stream(idx, a, (cudaStream_t)stream);
+  if (rc == FRS_OK) exchange_commit_push(ex);  // the sequence number advances only once the push is really enqueued
+  return rc;
+}
+
+// Pipelined search (device buffers): prep / scan / merge (+ exchange) run on the index's internal streams, so the
+// prep of call i+1 and the merge + exchange of call i-1 overlap the scan of call i.
+extern "C" int frs_index_search_async(frs_index* idx, frs_exchange* ex, const float* dev_queries,
+                                      const uint32_t* dev_q_code, const uint32_t* dev_q_mask, int nq, int k,
+                                      float* dev_out_scores, int64_t* dev_out_ids, void* in_stream, int* ticket) {
+  if (!idx || !dev_out_scores || !dev_out_ids || !ticket) return set_err(FRS_E_INVALID, "null pointer argument");
+  int rc = ex ? check_exchange_args(idx, ex, nq, k) : FRS_OK;
+  if (rc) return rc;
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  SearchArgs a;
+  a.q = dev_queries; a.code = dev_q_code; a.mask = dev_q_mask; a.nq = nq; a.k = k;
+  PushTarget t{};
+  if (ex) {
+    rc = exchange_begin_push(ex, nq, k, &t);  // refuses a poisoned exchange before anything is enqueued
+    if (rc) return rc;
+    a.out_s64 = reinterpret_cast<double*>(ex->local);
+    a.out_ids = reinterpret_cast<int64_t*>(ex->local) + ex->plane_words;
+    a.push = &t;
+  } else {
+    a.out_s32 = dev_out_scores;
+    a.out_ids = dev_out_ids;
+  }
+  SearchLaunch L{};
+  int slot = 0;
+  rc = pipelined_begin(idx, true, (cudaStream_t)in_stream, &slot, &L);
+  if (rc) return rc;
+  rc = search_enqueue(idx, a, L);
+  if (rc) return rc;
+  if (ex) {
+    exchange_commit_push(ex);
+    rc = exchange_wait_merge(ex, nq, k, dev_out_scores, dev_out_ids, idx->s_merge);
+    if (rc) return rc;
+  }
+  if (L.prof) {
+    CU_TRY(cudaEventRecord(L.prof[6], idx->s_merge));
+    idx->prof_calls++;
+  }
+  CU_TRY(cudaEventRecord(idx->job_done[slot], idx->s_merge));
+  idx->last_launches += ex ? 2 : 0;
+  *ticket = slot;
+  return FRS_OK;
+}
+
+extern "C" int frs_index_wait(frs_index* idx, int ticket, void* stream) {
+  if (!idx || ticket >= kJobRing) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (ticket < 0) {
+    if (idx->jobs == 0) return FRS_OK;
+    ticket = (int)((idx->jobs - 1) % kJobRing);  // the merge stream is in order: the newest job finishes last
+  }
+  CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, idx->job_done[ticket], 0));
+  return FRS_OK;
+}
+
+extern "C" int frs_index_sync(frs_index* idx, int ticket) {
+  if (!idx || ticket >= kJobRing) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (ticket < 0) {
+      if (idx->jobs == 0) return FRS_OK;
+      ticket = (int)((idx->jobs - 1) % kJobRing);
+    }
+    ev = idx->job_done[ticket];
+  }
+  CU_TRY(cudaEventSynchronize(ev));
+  return FRS_OK;
+}
+
+// Host-buffer search, split in two so that a caller (or several threads) can keep a few batches in flight: the
+// H2D copy of batch i+1 and the D2H copy of batch i-1 overlap the scan of batch i.  With `ex` the local result
+// is exchanged with the other ranks (every rank submits the same batches in the same order).
+extern "C" int frs_index_search_host_submit(frs_index* idx, frs_exchange* ex, const float* host_queries,
+                                            const uint32_t* host_q_code, const uint32_t* host_q_mask, int nq, int k,
+                                            int* ticket) {
+  if (!idx) return set_err(FRS_E_INVALID, "idx is null");
+  if (nq < 1 || nq > kNQ) return set_err(FRS_E_INVALID, "nq must be in [1,%d] (got %d)", kNQ, nq);
+  if (k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "k must be in [1,%d] (got %d)", kMaxK, k);
+  if (!host_queries || !host_q_code || !host_q_mask || !ticket) return set_err(FRS_E_INVALID, "null pointer argument");
+  int rc = ex ? check_exchange_args(idx, ex, nq, k) : FRS_OK;
+  if (rc) return rc;
+  CU_TRY(cudaSetDevice(idx->device));
+  int hsi = 0;
+  rc = host_slot_acquire(idx, &hsi);
+  if (rc) return rc;
+  HostSlot& h = idx->hs[hsi];
+  const size_t qb = (size_t)nq * kDim * 4;
+  memcpy(h.h_in, host_queries, qb);
+  memcpy(h.h_in + qb, host_q_code, (size_t)nq * 4);
+  memcpy(h.h_in + qb + (size_t)nq * 4, host_q_mask, (size_t)nq * 4);
+  h.nq = nq;
+  h.k = k;
+  auto fail = [&](int code) {
+    host_slot_release(idx, hsi);
+    return code;
+  };
+  std::lock_guard<std::mutex> lk(idx->mu);
+  int64_t* d_ids = reinterpret_cast<int64_t*>(h.d_out);
+  float* d_scores = reinterpret_cast<float*>(h.d_out + (size_t)nq * k * 8);
+  SearchArgs a;
+  a.q = reinterpret_cast<const float*>(h.d_in);
+  a.code = reinterpret_cast<const uint32_t*>(h.d_in + qb);
+  a.mask = a.code + nq;
+  a.nq = nq;
+  a.k = k;
+  PushTarget t{};
+  if (ex) {
+    rc = exchange_begin_push(ex, nq, k, &t);
+    if (rc) return fail(rc);
+    a.out_s64 = reinterpret_cast<double*>(ex->local);
+    a.out_ids = reinterpret_cast<int64_t*>(ex->local) + ex->plane_words;
+    a.push = &t;
+  } else {
+    a.out_s32 = d_scores;
+    a.out_ids = d_ids;
+  }
+  SearchLaunch L{};
+  int slot = 0;
+  rc = pipelined_begin(idx, false, nullptr, &slot, &L);
+  if (rc) return fail(rc);
+  cudaError_t e = cudaMemcpyAsync(h.d_in, h.h_in, qb + (size_t)nq * 8, cudaMemcpyHostToDevice, idx->s_prep);
+  if (e != cudaSuccess) return fail(set_err(FRS_E_CUDA, "cudaMemcpyAsync (queries): %s", cudaGetErrorString(e)));
+  rc = search_enqueue(idx, a, L);
+  if (rc) return fail(rc);
+  if (ex) {
+    exchange_commit_push(ex);
+    rc = exchange_wait_merge(ex, nq, k, d_scores, d_ids, idx->s_merge);
+    if (rc) return fail(rc);
+  }
+  if (L.prof) {
+    cudaEventRecord(L.prof[6], idx->s_merge);
+    idx->prof_calls++;
+  }
+  e = cudaMemcpyAsync(h.h_out, h.d_out, (size_t)nq * k * 12, cudaMemcpyDeviceToHost, idx->s_merge);
+  if (e == cudaSuccess) e = cudaEventRecord(h.done, idx->s_merge);
+  if (e == cudaSuccess) e = cudaEventRecord(idx->job_done[slot], idx->s_merge);
+  if (e != cudaSuccess) return fail(set_err(FRS_E_CUDA, "cudaMemcpyAsync (results): %s", cudaGetErrorString(e)));
+  idx->last_launches += ex ? 2 : 0;
+  *ticket = hsi;
+  return FRS_OK;
+}
+
+extern "C" int frs_index_search_host_collect(frs_index* idx, frs_exchange* ex, int ticket, float* host_out_scores,
+                                             int64_t* host_out_ids) {
+  if (!idx || ticket < 0 || ticket >= kHostSlots || !host_out_scores || !host_out_ids)
+    return set_err(FRS_E_INVALID, "bad argument");
+  HostSlot& h = idx->hs[ticket];
+  if (!h.busy) return set_err(FRS_E_STATE, "ticket %d is not in flight", ticket);
+  CU_TRY(cudaSetDevice(idx->device));
+  cudaError_t e = cudaEventSynchronize(h.done);
+  int rc = FRS_OK;
+  if (e != cudaSuccess) rc = set_err(FRS_E_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+  if (rc == FRS_OK && ex) rc = exchange_check(ex);
+  if (rc == FRS_OK) {
+    memcpy(host_out_ids, h.h_out, (size_t)h.nq * h.k * 8);
+    memcpy(host_out_scores, h.h_out + (size_t)h.nq * h.k * 8, (size_t)h.nq * h.k * 4);
+  }
+  host_slot_release(idx, ticket);
+  return rc;
 }
 
 extern "C" int frs_index_search_host(frs_index* idx, const float* host_queries, const uint32_t* host_q_code,
                                      const uint32_t* host_q_mask, int nq, int k, float* host_out_scores,
                                      int64_t* host_out_ids) {
-  if (!idx) return set_err(FRS_E_INVALID, "idx is null");
-  if (nq < 1 || nq > kNQ) return set_err(FRS_E_INVALID, "nq must be in [1,%d] (got %d)", kNQ, nq);
-  if (k < 1 || k > kMaxK) return set_err(FRS_E_INVALID, "k must be in [1,%d] (got %d)", kMaxK, k);
-  if (!host_queries || !host_q_code || !host_q_mask || !host_out_scores || !host_out_ids)
-    return set_err(FRS_E_INVALID, "null pointer argument");
-  CU_TRY(cudaSetDevice(idx->device));
-  // the pinned staging buffers belong to the index: one host-call at a time
-  static std::mutex host_mu;
-  std::lock_guard<std::mutex> lk(host_mu);
-  memcpy(idx->h_q, host_queries, (size_t)nq * kDim * 4);
-  memcpy(idx->h_code, host_q_code, (size_t)nq * 4);
-  memcpy(idx->h_mask, host_q_mask, (size_t)nq * 4);
-  cudaStream_t st = idx->stream;
-  CU_TRY(cudaMemcpyAsync(idx->d_q, idx->h_q, (size_t)nq * kDim * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(idx->d_code, idx->h_code, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(idx->d_mask, idx->h_mask, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-  int rc = search_impl(idx, idx->d_q, idx->d_code, idx->d_mask, nq, k, idx->d_out_s, nullptr, idx->d_out_ids, st);
+  if (!host_out_scores || !host_out_ids) return set_err(FRS_E_INVALID, "null pointer argument");
+  int ticket = -1;
+  int rc = frs_index_search_host_submit(idx, nullptr, host_queries, host_q_code, host_q_mask, nq, k, &ticket);
   if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(idx->h_out_s, idx->d_out_s, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(idx->h_out_ids, idx->d_out_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
-  memcpy(host_out_scores, idx->h_out_s, (size_t)nq * k * 4);
-  memcpy(host_out_ids, idx->h_out_ids, (size_t)nq * k * 8);
-  return FRS_OK;
+  return frs_index_search_host_collect(idx, nullptr, ticket, host_out_scores, host_out_ids);
 }
 
 extern "C" int frs_merge_shards(int device, const double* dev_scores64, const int64_t* dev_ids, int n_shards,
@@ -641,8 +915,10 @@ extern "C" int frs_merge_shards_packed(int device, const int64_t* dev_packed, in
 extern "C" int frs_index_last_queries(frs_index* idx, float* dev_out, void* stream) {
   if (!idx || !dev_out) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
-  CU_TRY(cudaMemcpyAsync(dev_out, idx->qrec, (size_t)kNQ * kDim * 4, cudaMemcpyDeviceToDevice,
-                         (cudaStream_t)stream));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  const SearchWs& w = idx->ws[idx->ws_last];
+  CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, w.free, 0));
+  CU_TRY(cudaMemcpyAsync(dev_out, w.qrec, (size_t)kNQ * kDim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return FRS_OK;
 }
 
@@ -654,10 +930,14 @@ extern "C" int frs_index_debug_scores(frs_index* idx, const float* dev_queries, 
   std::lock_guard<std::mutex> lk(idx->mu);
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = idx->f32();
-  CU_TRY(cudaStreamWaitEvent(st, idx->ws_free, 0));
-  CU_TRY(cudaMemsetAsync(idx->d_code, 0, kNQ * 4, st));
-  CU_TRY(launch_prep_queries(f32, dev_queries, idx->d_code, idx->d_code, nq, idx->qop, idx->qrec, idx->qcode,
-                             idx->qmask, idx->stats, idx->gmax, idx->gsample, idx->rows, idx->codes, (uint32_t)idx->size, st));
+  SearchWs& w = idx->ws[idx->ws_next];
+  idx->ws_last = idx->ws_next;
+  idx->ws_next = (idx->ws_next + 1) % kWsRing;
+  CU_TRY(cudaStreamWaitEvent(st, w.free, 0));
+  CU_TRY(cudaStreamWaitEvent(st, idx->rows_ready, 0));
+  CU_TRY(cudaMemsetAsync(w.qcode, 0, kNQ * 4, st));  // all-zero (code, mask): every row passes the predicate
+  CU_TRY(launch_prep_queries(f32, dev_queries, w.qcode, w.qcode, nq, w.qop, w.qrec, w.qcode, w.qmask, w.stats, w.gmax,
+                             w.gsample, idx->rows, idx->codes, (uint32_t)idx->size, st));
   const uint32_t n = (uint32_t)idx->size;
   const uint32_t num_tiles = (n + kTileM - 1) / kTileM;
   const int grid = scan_grid(idx, num_tiles);
@@ -667,19 +947,19 @@ extern "C" int frs_index_debug_scores(frs_index* idx, const float* dev_queries, 
     sp.codes = idx->codes;
     sp.n = n;
     sp.num_tiles = num_tiles;
-    sp.qrec = idx->qrec;
-    sp.qcode = idx->qcode;
-    sp.qmask = idx->qmask;
+    sp.qrec = w.qrec;
+    sp.qcode = w.qcode;
+    sp.qmask = w.qmask;
     sp.nq = nq;
     sp.k = 1;
     sp.eps = 0.f;
     sp.dbg_scores = dev_out;
-    sp.gmax = idx->gmax;
-    sp.gsample = idx->gsample;
-    sp.stats = idx->stats;
-    CU_TRY(launch_scan(f32, true, grid, idx->tmap_rows, idx->tmap_q, sp, st));
+    sp.gmax = w.gmax;
+    sp.gsample = w.gsample;
+    sp.stats = w.stats;
+    CU_TRY(launch_scan(f32, true, grid, idx->tmap_rows, w.tmap_q, sp, st));
   }
-  CU_TRY(cudaEventRecord(idx->ws_free, st));
+  CU_TRY(cudaEventRecord(w.free, st));
   return FRS_OK;
 }
 
@@ -687,7 +967,13 @@ extern "C" int frs_index_last_stats(frs_index* idx, int64_t* host_out6) {
   if (!idx || !host_out6) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
   unsigned long long h[kStatSlots];
-  CU_TRY(cudaMemcpy(h, idx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+  const SearchWs* w;
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    w = &idx->ws[idx->ws_last];
+  }
+  CU_TRY(cudaEventSynchronize(w->free));
+  CU_TRY(cudaMemcpy(h, w->stats, sizeof(h), cudaMemcpyDeviceToHost));
   host_out6[0] = (int64_t)h[kStatAppended];
   host_out6[1] = (int64_t)h[kStatCompactions];
   host_out6[2] = (int64_t)h[kStatResolutions];
@@ -701,43 +987,86 @@ extern "C" int frs_index_last_stats(frs_index* idx, int64_t* host_out6) {
 // profiling
 // ---------------------------------------------------------------------------------------------
 extern "C" int frs_index_set_profiling(frs_index* idx, int mode) {
-  if (!idx || mode < 0 || mode > 2) return set_err(FRS_E_INVALID, "bad argument");
+  if (!idx || mode < 0 || mode > 3) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
   std::lock_guard<std::mutex> lk(idx->mu);
-  if (mode && !idx->prof_ev) {
-    idx->prof_ev = new (std::nothrow) cudaEvent_t[frs_index::kProfRing * 4];
+  if (mode == 3 && !idx->br_first) {
+    CU_TRY(cudaEventCreate(&idx->br_first));
+    CU_TRY(cudaEventCreate(&idx->br_last));
+  }
+  idx->br_count = 0;
+  if (mode && mode != 3 && !idx->prof_ev) {
+    idx->prof_ev = new (std::nothrow) cudaEvent_t[frs_index::kProfRing * kProfEvents];
     if (!idx->prof_ev) return set_err(FRS_E_INVALID, "out of host memory");
-    for (int i = 0; i < frs_index::kProfRing * 4; ++i) CU_TRY(cudaEventCreate(&idx->prof_ev[i]));
+    for (int i = 0; i < frs_index::kProfRing * kProfEvents; ++i) CU_TRY(cudaEventCreate(&idx->prof_ev[i]));
   }
   idx->prof_mode = mode;
   idx->prof_calls = 0;
   return FRS_OK;
 }
 
-extern "C" int frs_index_read_profile(frs_index* idx, double* host_out4) {
-  if (!idx || !host_out4) return set_err(FRS_E_INVALID, "bad argument");
+// out8: {searches, prep ms, scan ms, merge ms, exchange ms (cross-shard wait + merge; 0 for a plain search),
+//        scan-stream gap ms (end of one scan kernel -> start of the next, summed over consecutive searches),
+//        span ms (first prep start -> last search end), 0}
+extern "C" int frs_index_read_profile_ex(frs_index* idx, double* host_out8) {
+  if (!idx || !host_out8) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
   std::lock_guard<std::mutex> lk(idx->mu);
-  host_out4[0] = host_out4[1] = host_out4[2] = host_out4[3] = 0.0;
+  for (int i = 0; i < 8; ++i) host_out8[i] = 0.0;
+  if (idx->prof_mode == 3) {  // bracket: {scans, 0, bracket ms (first scan start -> last scan end), 0...}
+    if (idx->br_count == 0) return FRS_OK;
+    CU_TRY(cudaEventSynchronize(idx->br_last));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, idx->br_first, idx->br_last));
+    host_out8[0] = idx->br_count;
+    host_out8[2] = ms;
+    host_out8[6] = ms;
+    idx->br_count = 0;
+    return FRS_OK;
+  }
   if (!idx->prof_ev || idx->prof_calls == 0) return FRS_OK;
   const int n = idx->prof_calls < frs_index::kProfRing ? idx->prof_calls : frs_index::kProfRing;
+  auto evs = [&](int c) {  // c = 0 is the newest recorded search
+    return idx->prof_ev + (size_t)((idx->prof_calls - 1 - c) % frs_index::kProfRing) * kProfEvents;
+  };
+  CU_TRY(cudaEventSynchronize(evs(0)[6]));
   for (int c = 0; c < n; ++c) {
-    cudaEvent_t* ev = idx->prof_ev + (size_t)((idx->prof_calls - 1 - c) % frs_index::kProfRing) * 4;
-    CU_TRY(cudaEventSynchronize(ev[3]));
-    for (int j = 0; j < 3; ++j) {
-      float ms = 0.f;
-      CU_TRY(cudaEventElapsedTime(&ms, ev[j], ev[j + 1]));
-      host_out4[1 + j] += ms;
+    cudaEvent_t* ev = evs(c);
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    host_out8[1] += ms;
+    CU_TRY(cudaEventElapsedTime(&ms, ev[2], ev[3]));
+    host_out8[2] += ms;
+    CU_TRY(cudaEventElapsedTime(&ms, ev[4], ev[5]));
+    host_out8[3] += ms;
+    CU_TRY(cudaEventElapsedTime(&ms, ev[5], ev[6]));
+    host_out8[4] += ms;
+    if (c + 1 < n) {
+      CU_TRY(cudaEventElapsedTime(&ms, evs(c + 1)[3], ev[2]));
+      host_out8[5] += ms > 0.f ? ms : 0.f;
     }
   }
-  host_out4[0] = n;
+  float span = 0.f;
+  CU_TRY(cudaEventElapsedTime(&span, evs(n - 1)[0], evs(0)[6]));
+  host_out8[6] = span;
+  host_out8[0] = n;
   idx->prof_calls = 0;
+  return FRS_OK;
+}
+
+extern "C" int frs_index_read_profile(frs_index* idx, double* host_out4) {
+  if (!host_out4) return set_err(FRS_E_INVALID, "bad argument");
+  double o[8];
+  int rc = frs_index_read_profile_ex(idx, o);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) host_out4[i] = o[i];
   return FRS_OK;
 }
 
 extern "C" int frs_index_read_timeline(frs_index* idx, uint64_t* host_out, int n_ctas) {
   if (!idx || !host_out || n_ctas < 0 || n_ctas > kGmaxPad) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
+  CU_TRY(cudaDeviceSynchronize());
   CU_TRY(cudaMemcpy(host_out, idx->timeline, (size_t)n_ctas * 16 * 8, cudaMemcpyDeviceToHost));
   return FRS_OK;
 }

@@ -698,10 +698,14 @@ __device__ __forceinline__ Best block_max_best(Best v, Best* red /*[8]*/) {
   return m;
 }
 
-size_t merge_smem_bytes(int nparts) {
-  const size_t ent = (size_t)(nparts > 0 ? nparts : 1) * kListCap;
-  return ent * (8 /*survivor keys*/ + 8 /*band exact*/ + 4 /*band rows*/) + 64;
-}
+// The merge kernel keeps survivors / band scores / band rows (20 B per entry) in shared memory when the CTAs'
+// lists hold at most kMergeSmemEnt entries for the query in total — the normal case is a few dozen — so that
+// the kernel's 32 CTAs fit next to a running scan on the SMs it leaves free (pipelined search).  Fuller lists
+// (adversarial: millions of near-duplicates) use the per-query spill area in global memory instead.
+constexpr int kMergeSmemEnt = 1536;
+constexpr size_t kMergeEntBytes = 8 /*survivor keys*/ + 8 /*band exact*/ + 4 /*band rows*/;
+size_t merge_smem_bytes(int) { return (size_t)kMergeSmemEnt * kMergeEntBytes + 64; }
+size_t merge_spill_bytes() { return (size_t)kNQ * kGmaxPad * kListCap * kMergeEntBytes; }
 
 // up to 4 exact scores at once (same arithmetic and summation order as exact_dot; the loads of all
 // rows are issued before the first use so the DRAM latency is paid once per group)
@@ -761,6 +765,13 @@ __device__ __forceinline__ void exact_dot4(const void* __restrict__ rows, const 
   }
 }
 
+// local row -> global id (MergeParams): contiguous shard or block-cyclic shard
+__device__ __forceinline__ int64_t global_id(const MergeParams& p, uint32_t row) {
+  if (p.id_block == 0u) return p.base + (int64_t)row;
+  const uint32_t blk = row / p.id_block;
+  return ((int64_t)blk * p.id_shards + p.id_shard) * (int64_t)p.id_block + (int64_t)(row - blk * p.id_block);
+}
+
 constexpr uint32_t kRankCountMax = 512;  // above this many entries selection falls back to k rounds
 
 // One CTA per query.
@@ -772,19 +783,27 @@ template <bool F32>
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams p) {
   extern __shared__ __align__(16) uint8_t msm[];
   const int q = blockIdx.x;
-  const int maxent = (p.nparts > 0 ? p.nparts : 1) * kListCap;
-  uint64_t* surv = reinterpret_cast<uint64_t*>(msm);
-  double* band_x = reinterpret_cast<double*>(surv + maxent);
-  uint32_t* band_row = reinterpret_cast<uint32_t*>(band_x + maxent);
   __shared__ Best red[kMergeThreads / 32];
   __shared__ uint32_t cnt_s[kGmaxPad];
-  __shared__ uint32_t n_surv, n_band;
+  __shared__ uint32_t n_surv, n_band, n_total;
   __shared__ uint64_t ak_s;
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const int k = p.k;
-  if (tid == 0) { n_surv = 0; n_band = 0; ak_s = 0ull; }
-  if (tid < p.nparts) cnt_s[tid] = p.part_cnt[tid * kNQ + q];
+  if (tid == 0) { n_surv = 0; n_band = 0; ak_s = 0ull; n_total = 0; }
+  __syncthreads();
+  if (tid < p.nparts) {
+    const uint32_t c = min(p.part_cnt[tid * kNQ + q], (uint32_t)kListCap);
+    cnt_s[tid] = c;
+    atomicAdd(&n_total, c);
+  }
+  __syncthreads();
+  const bool spill = n_total > (uint32_t)kMergeSmemEnt;
+  const int maxent = spill ? kGmaxPad * kListCap : kMergeSmemEnt;
+  uint8_t* area = spill ? p.spill + (size_t)q * kGmaxPad * kListCap * kMergeEntBytes : msm;
+  uint64_t* surv = reinterpret_cast<uint64_t*>(area);
+  double* band_x = reinterpret_cast<double*>(surv + maxent);
+  uint32_t* band_row = reinterpret_cast<uint32_t*>(band_x + maxent);
 
   // 1. coarse cut (computed redundantly by every warp: no block-level exchange needed)
   float thr0 = -INFINITY;
@@ -875,7 +894,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
         const size_t o = (size_t)q * k + rank;
         if (p.out_s64) p.out_s64[o] = xi;
         if (p.out_s32) p.out_s32[o] = (float)xi;
-        p.out_ids[o] = p.base + (int64_t)ri;
+        p.out_ids[o] = global_id(p, ri);
       }
     }
   } else {
@@ -892,7 +911,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
         const double sc = f64_from_ordered(m.hi);
         if (p.out_s64) p.out_s64[o] = sc;
         if (p.out_s32) p.out_s32[o] = (float)sc;
-        p.out_ids[o] = p.base + (int64_t)(~m.lo);
+        p.out_ids[o] = global_id(p, ~m.lo);
       }
       pb = m;
     }
@@ -908,14 +927,13 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
     // of every peer's gather buffer over NVLink peer memory (plain stores through IPC-mapped pointers).
     __syncthreads();  // this CTA's results are in p.out_s64 / p.out_ids
     const PushTarget& t = p.push;
-    const size_t plane = (size_t)t.nq_stride * k;
     const size_t slot = ((size_t)(t.seq % kExchangeSlots) * t.world + t.rank) * t.block_words;
     const uint64_t* s64 = reinterpret_cast<const uint64_t*>(p.out_s64);
     const uint64_t* ids = reinterpret_cast<const uint64_t*>(p.out_ids);
-    for (uint32_t i = tid; i < (uint32_t)(t.world * 2 * k); i += kMergeThreads) {
+    for (uint32_t i = tid; i < (uint32_t)(t.n_targets * 2 * k); i += kMergeThreads) {
       const uint32_t peer = i / (2 * k), w = i % (2 * k), pl = w / k, r = w % k;
       const size_t o = (size_t)q * k + r;
-      t.peer_gather[peer][slot + pl * plane + o] = pl ? ids[o] : s64[o];
+      t.peer_gather[peer][slot + pl * t.plane_words + o] = pl ? ids[o] : s64[o];
     }
     __syncthreads();
     __shared__ unsigned int s_last;
@@ -929,8 +947,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
     __syncthreads();
     if (s_last) {  // every other CTA has fenced its stores and been counted: publish the sequence number
       if (tid == 0) *t.counter = 0;  // next launch (stream-ordered)
-      for (uint32_t peer = tid; peer < (uint32_t)t.world; peer += kMergeThreads)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flags[peer] + t.rank), "r"(t.seq) : "memory");
+      if (t.peer_flags)
+        for (uint32_t peer = tid; peer < (uint32_t)t.n_targets; peer += kMergeThreads)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flags[peer] + t.rank), "r"(t.seq) : "memory");
     }
   }
 }
@@ -940,10 +959,18 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
 // ---------------------------------------------------------------------------------------------
 __global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_t* __restrict__ ids,
                                     int n_shards, int nq, int k, size_t shard_stride,
-                                    float* __restrict__ out_s32, int64_t* __restrict__ out_ids) {
+                                    float* __restrict__ out_s32, int64_t* __restrict__ out_ids,
+                                    const uint32_t* __restrict__ poison) {
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
   const int total = n_shards * k;
+  if (poison && __ldcg(poison) != 0u) {  // the exchange timed out: never hand out a partially gathered result
+    for (int r = lane; r < k; r += 32) {
+      out_s32[(size_t)q * k + r] = -INFINITY;
+      out_ids[(size_t)q * k + r] = -1;
+    }
+    return;
+  }
   // each lane owns candidates lane, lane+32, ... ; rank = number of strictly better candidates
   for (int c = lane; c < total; c += 32) {
     const int sh = c / k, j = c - sh * k;
@@ -1140,7 +1167,7 @@ __global__ void store_rows_kernel(const float* __restrict__ vecs, const uint32_t
     if constexpr (F32) reinterpret_cast<float*>(rows_dst)[o] = y;
     else reinterpret_cast<__nv_bfloat16*>(rows_dst)[o] = __float2bfloat16_rn(y);
   }
-  if (lane == 0) codes_dst[row] = codes ? codes[row] : 0u;
+  if (lane == 0 && codes_dst) codes_dst[row] = codes ? codes[row] : 0u;
 }
 
 template <bool F32>
@@ -1179,22 +1206,27 @@ cudaError_t launch_scan(bool f32, bool dump, int grid, const CUtensorMap& tr, co
 
 cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st) {
   const size_t smem = merge_smem_bytes(p.nparts);
-  cudaError_t e;
-  if (f32) {
-    e = cudaFuncSetAttribute(merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the opt-in limit is set once per device to what the largest grid (kGmaxPad parts) needs
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    const int lim = (int)merge_smem_bytes(kGmaxPad);
+    e = cudaFuncSetAttribute(merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
-    merge_kernel<true><<<p.nq, kMergeThreads, smem, st>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    merge_kernel<false><<<p.nq, kMergeThreads, smem, st>>>(p);
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
+  if (f32) merge_kernel<true><<<p.nq, kMergeThreads, smem, st>>>(p);
+  else merge_kernel<false><<<p.nq, kMergeThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
-                                size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st) {
-  merge_shards_kernel<<<nq, 32, 0, st>>>(s64, ids, n_shards, nq, k, shard_stride, out_s32, out_ids);
+                                size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st,
+                                const uint32_t* poison) {
+  merge_shards_kernel<<<nq, 32, 0, st>>>(s64, ids, n_shards, nq, k, shard_stride, out_s32, out_ids, poison);
   return cudaGetLastError();
 }
 
@@ -1221,6 +1253,25 @@ cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, 
     prep_queries_kernel<false><<<kSampleBlocks, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
                                                                       gmax, gsample, rows, codes, n);
   return cudaGetLastError();
+}
+
+// CUDA loads a kernel's code lazily, at its first launch, and that load synchronises with the device.  A first
+// launch that happens while an exchange-wait kernel is spinning for a peer (whose own work is queued behind the
+// load) would stall until the wait times out — so every kernel of the search path is loaded when an index is created.
+cudaError_t preload_search_kernels() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)scan_kernel<false, false>, (const void*)scan_kernel<true, false>,
+                       (const void*)scan_kernel<false, true>,  (const void*)scan_kernel<true, true>,
+                       (const void*)merge_kernel<false>,       (const void*)merge_kernel<true>,
+                       (const void*)merge_shards_kernel,       (const void*)prep_queries_kernel<false>,
+                       (const void*)prep_queries_kernel<true>, (const void*)store_rows_kernel<false>,
+                       (const void*)store_rows_kernel<true>,   (const void*)read_rows_kernel<false>,
+                       (const void*)read_rows_kernel<true>};
+  for (const void* f : fns) {
+    cudaError_t e = cudaFuncGetAttributes(&a, f);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_store_rows(bool f32, const float* vecs, const uint32_t* codes, int64_t n,

@@ -67,13 +67,15 @@ struct ScanParams {
 constexpr uint32_t kExchangeSlots = 4;
 
 struct PushTarget {
-  uint64_t* const* peer_gather;  // device array [world], null = no push
-  uint32_t* const* peer_flags;   // device array [world]
+  uint64_t* const* peer_gather;  // device array [n_targets] of gather buffers, null = no push
+  uint32_t* const* peer_flags;   // device array [n_targets] of flag arrays, or null: no flags are published (one process
+                                 // driving several GPUs orders the consumer with CUDA events instead, csrc/sharded.cu)
   unsigned int* counter;         // CTAs done (local, self-resetting)
-  int world, rank;
+  int n_targets;                 // how many buffers receive this rank's block (world, or 1 = only the collecting GPU)
+  int world, rank;               // the block lands in slot `rank` of `world`
   uint32_t seq;
   size_t block_words;            // 2 * nq_max * k_max
-  int nq_stride;                 // nq_max of the exchange (plane = nq_max * k)
+  size_t plane_words;            // nq_max * k_max: offset of the id plane inside a block
 };
 
 struct MergeParams {
@@ -86,24 +88,33 @@ struct MergeParams {
   int nq;
   int k;
   float eps;
-  int64_t base;        // global id of local row 0
+  int64_t base;        // global id of local row 0 (contiguous shards)
+  // block-cyclic shards (csrc/sharded.cu): local row r is global row ((r / id_block) * id_shards + id_shard) * id_block
+  // + r % id_block; id_block == 0 selects base + r.  Monotone in r, so local ties (row asc) are global ties (id asc).
+  uint32_t id_block;
+  uint32_t id_shards, id_shard;
   double* out_s64;     // [nq, k] or null
   float* out_s32;      // [nq, k] or null
   int64_t* out_ids;    // [nq, k]
   unsigned long long* stats;
+  uint8_t* spill;      // [merge_spill_bytes()] global scratch for queries whose lists exceed the shared-memory area
   PushTarget push;
 };
 
+cudaError_t preload_search_kernels();
 size_t scan_smem_bytes(bool f32);
 size_t merge_smem_bytes(int nparts);
+size_t merge_spill_bytes();
 
 // all launchers return the cudaError_t of configuration + launch
 cudaError_t launch_scan(bool f32, bool dump, int grid, const CUtensorMap& tmap_rows,
                         const CUtensorMap& tmap_q, const ScanParams& p, cudaStream_t st);
 cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st);
 // shard_stride: elements between consecutive shards in both arrays (nq*k when they are dense)
+// poison: optional device word; non-zero = the exchange that filled the buffer timed out -> every slot is emitted empty
 cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
-                                size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st);
+                                size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st,
+                                const uint32_t* poison = nullptr);
 // queries [nq,384] fp32 -> qop (MMA operand, bf16 or tf32-rounded fp32, zero padded to 32 rows),
 // qrec (fp32 record copy), qcode/qmask copies padded to 32
 // also scores a strided sample of the stored rows against the prepared queries (bootstrap bound)

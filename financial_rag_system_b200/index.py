@@ -29,6 +29,27 @@ def _stream_ptr(device: torch.device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class PendingSearch:
+    """Result of a pipelined search: `ids` / `scores` are valid once the ticket has been waited for."""
+
+    def __init__(self, index, ticket: int, ids, scores, keep=()):
+        self._index, self.ticket, self.ids, self.scores, self._keep = index, ticket, ids, scores, keep
+
+    def wait(self):
+        """Block the host until the results are complete; returns (ids, scores)."""
+        if self._index is not None:
+            self._index.sync(self.ticket)
+            self._index = None
+        self._keep = ()
+        return self.ids, self.scores
+
+    def wait_stream(self):
+        """Make the current CUDA stream wait for the results (no host block); returns (ids, scores)."""
+        if self._index is not None:
+            self._index.wait(self.ticket)
+        return self.ids, self.scores
+
+
 class VectorIndex:
     """One shard: `capacity` rows x 384, stored L2-normalised in bf16 or fp32 on one GPU."""
 
@@ -84,14 +105,15 @@ class VectorIndex:
             c = None if codes is None else np.ascontiguousarray(codes).astype(np.uint32)
             check(self._lib.frs_index_add_host(self._h, _ptr(v), _ptr(c), v.shape[0]))
 
-    def set_rows(self, row0: int, vecs: torch.Tensor, codes: torch.Tensor | None = None) -> None:
-        v = vecs.to(device=self.device, dtype=torch.float32).contiguous()
-        c = None if codes is None else codes.to(device=self.device, dtype=torch.int32).contiguous()
+    def set_rows(self, row0: int, vecs, codes=None) -> None:
+        """Overwrite rows in place (torch tensors or numpy); codes=None keeps the stored payload codes."""
+        v = torch.as_tensor(vecs).to(device=self.device, dtype=torch.float32).contiguous()
+        c = None if codes is None else self._as_code_tensor(codes)
         check(self._lib.frs_index_set_rows(self._h, int(row0), _ptr(v), _ptr(c), v.shape[0], _stream_ptr(self.device)))
         torch.cuda.current_stream(self.device).synchronize()
 
-    def set_codes(self, row0: int, codes: torch.Tensor) -> None:
-        c = codes.to(device=self.device, dtype=torch.int32).contiguous()
+    def set_codes(self, row0: int, codes) -> None:
+        c = self._as_code_tensor(codes)
         check(self._lib.frs_index_set_codes(self._h, int(row0), _ptr(c), c.numel(), _stream_ptr(self.device)))
         torch.cuda.current_stream(self.device).synchronize()
 
@@ -121,6 +143,10 @@ class VectorIndex:
 
     def set_scan_grid(self, grid: int) -> None:
         check(self._lib.frs_index_set_scan_grid(self._h, int(grid)))
+
+    def set_pipeline_reserve(self, sms: int) -> None:
+        """SMs the persistent scan kernel leaves to the prep / merge / exchange kernels in the pipelined forms."""
+        check(self._lib.frs_index_set_pipeline_reserve(self._h, int(sms)))
 
     # -- search ---------------------------------------------------------------------------------
     @staticmethod
@@ -157,6 +183,54 @@ class VectorIndex:
         scores = np.empty((nq, k), dtype=np.float32)
         ids = np.empty((nq, k), dtype=np.int64)
         check(self._lib.frs_index_search_host(self._h, _ptr(q), _ptr(qc), _ptr(qm), nq, k, _ptr(scores), _ptr(ids)))
+        return ids, scores
+
+    # -- pipelined forms (frs_index_search_async / _host_submit / _host_collect) ------------------
+    def search_async(self, queries: torch.Tensor, q_code: torch.Tensor, q_mask: torch.Tensor, k: int = 15,
+                     exchange=None) -> PendingSearch:
+        """Pipelined search of device tensors: prep / scan / merge run on the index's internal streams, so
+        consecutive calls overlap (the scans run back to back).  Inputs are read in current-stream order.
+        `exchange`: a sharded.PeerExchange — the result is then the global top-k over all ranks."""
+        q = queries.to(device=self.device, dtype=torch.float32).contiguous()
+        nq = q.shape[0]
+        self._check_batch(nq, k)
+        qc = q_code if (q_code.dtype == torch.int32 and q_code.device == self.device) else self._as_code_tensor(q_code)
+        qm = q_mask if (q_mask.dtype == torch.int32 and q_mask.device == self.device) else self._as_code_tensor(q_mask)
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        ticket = C.c_int(-1)
+        check(self._lib.frs_index_search_async(self._h, exchange._h if exchange is not None else None, _ptr(q), _ptr(qc),
+                                               _ptr(qm), nq, k, _ptr(scores), _ptr(ids), _stream_ptr(self.device),
+                                               C.byref(ticket)))
+        return PendingSearch(self, ticket.value, ids, scores, keep=(q, qc, qm))
+
+    def wait(self, ticket: int = -1) -> None:
+        """The current stream waits for a pipelined search (-1: everything submitted so far)."""
+        check(self._lib.frs_index_wait(self._h, int(ticket), _stream_ptr(self.device)))
+
+    def sync(self, ticket: int = -1) -> None:
+        check(self._lib.frs_index_sync(self._h, int(ticket)))
+
+    def submit_host(self, queries: np.ndarray, q_code: np.ndarray, q_mask: np.ndarray, k: int = 15, exchange=None) -> int:
+        """Host buffers in; returns a ticket for collect_host.  Up to 4 batches in flight per index."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        self._check_batch(nq, k)
+        qc = np.ascontiguousarray(np.asarray(q_code, dtype=np.int64).astype(np.uint32))
+        qm = np.ascontiguousarray(np.asarray(q_mask, dtype=np.int64).astype(np.uint32))
+        ticket = C.c_int(-1)
+        check(self._lib.frs_index_search_host_submit(self._h, exchange._h if exchange is not None else None, _ptr(q),
+                                                     _ptr(qc), _ptr(qm), nq, k, C.byref(ticket)))
+        self._pending_shape = getattr(self, "_pending_shape", {})
+        self._pending_shape[ticket.value] = (nq, k)
+        return ticket.value
+
+    def collect_host(self, ticket: int, exchange=None):
+        nq, k = self._pending_shape.pop(ticket)
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        check(self._lib.frs_index_search_host_collect(self._h, exchange._h if exchange is not None else None, int(ticket),
+                                                      _ptr(scores), _ptr(ids)))
         return ids, scores
 
     def search_tiles(self, queries, q_code, q_mask, k: int, tile_ids):
@@ -223,6 +297,16 @@ class VectorIndex:
         buf = (C.c_double * 4)()
         check(self._lib.frs_index_read_profile(self._h, buf))
         return {"n": int(buf[0]), "prep_ms": buf[1], "scan_ms": buf[2], "merge_ms": buf[3]}
+
+    def read_profile_ex(self) -> dict:
+        """read_profile plus 'exchange_ms' (cross-shard wait + merge), 'scan_gap_ms' (idle time of the scan stream
+        between consecutive scan kernels) and 'span_ms' (first prep start to last search end)."""
+        buf = (C.c_double * 8)()
+        check(self._lib.frs_index_read_profile_ex(self._h, buf))
+        keys = ("n", "prep_ms", "scan_ms", "merge_ms", "exchange_ms", "scan_gap_ms", "span_ms")
+        d = dict(zip(keys, [float(x) for x in buf]))
+        d["n"] = int(d["n"])
+        return d
 
     def read_timeline(self, n_ctas: int) -> np.ndarray:
         out = np.zeros((n_ctas, 16), dtype=np.uint64)

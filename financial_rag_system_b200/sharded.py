@@ -12,8 +12,10 @@ is balanced.  A search is
     final merge   [world, nq, k] -> [nq, k] by (score desc, id asc) on every rank      [CUDA]
 
 The per-shard lists are exact, so the result is identical to a single-shard search of the whole
-corpus whatever the number of shards.  The exchange + final merge of batch i run on a side stream
-and overlap the local pass of batch i+1 (`search_async`).
+corpus whatever the number of shards.  `search_async` is the pipelined form: ONE call into the library
+per batch (frs_index_search_async with the exchange) enqueues prep / scan / merge+push / wait+merge on the
+index's internal streams, so the scans of consecutive batches run back to back and everything else —
+including the exchange — hides behind them; no NCCL kernel is in the data path.
 
 The reference has no counterpart (one Qdrant server, main.py:215-239); this is north-star item (3).
 `local_search` / `merge` are injectable so that the host-side logic (partitioning, gather layout,
@@ -35,7 +37,7 @@ def shard_range(total_rows: int, rank: int, world: int) -> tuple[int, int]:
 
 
 class PendingSearch:
-    """Result of search_async: tensors are valid once `ready` has been waited on."""
+    """Result of search_async (all-gather form): tensors are valid once `ready` has been waited on."""
 
     def __init__(self, ids: torch.Tensor, scores: torch.Tensor, ready):
         self.ids, self.scores, self._ready = ids, scores, ready
@@ -45,13 +47,20 @@ class PendingSearch:
             self._ready.synchronize()
         return self.ids, self.scores
 
+    def wait_stream(self):
+        if self._ready is not None:
+            torch.cuda.current_stream(self.ids.device).wait_event(self._ready)
+        return self.ids, self.scores
+
 
 class PeerExchange:
     """The exchange step over NVLink peer memory (include/frs_b200.h frs_exchange_*): push = this rank's
-    [2, nq, k] block into every peer's gather buffer + a sequence flag; wait_merge = wait for all ranks' flags,
-    then the cross-shard merge.  One object per (nq, k).  Every rank calls push / wait_merge once per batch."""
+    block into every peer's gather buffer + a sequence flag; wait_merge = wait for all ranks' flags, then the
+    cross-shard merge.  ONE object serves every batch size <= nq and limit <= k (default 32 / 16 = the ABI's
+    maxima), so nothing is created in the request path.  Every rank pushes / merges once per batch, same order."""
 
-    def __init__(self, device: torch.device, world: int, rank: int, nq: int, k: int, group=None, connect: bool = True):
+    def __init__(self, device: torch.device, world: int, rank: int, nq: int = 32, k: int = 16, group=None,
+                 connect: bool = True, timeout_ms: Optional[int] = None):
         import ctypes as C
 
         from . import _lib
@@ -62,6 +71,8 @@ class PeerExchange:
         if not connect:
             _lib.check(_lib.lib().frs_exchange_create(device.index or 0, self.world, self.rank, self.nq, self.k, C.byref(h)))
             self._h = h
+            if timeout_ms:
+                self.set_timeout_ms(timeout_ms)
             return
         # Collective set-up: every rank takes part in the handle all-gather and in the final agreement even if one
         # of its own steps failed (CUDA IPC can be unavailable, e.g. in a restricted container), so that no rank is
@@ -88,6 +99,8 @@ class PeerExchange:
         if int(ok.item()) == 0:
             self.close()
             raise RuntimeError(f"peer-memory exchange unavailable on at least one rank (this rank: {err})")
+        if timeout_ms:
+            self.set_timeout_ms(timeout_ms)
 
     @staticmethod
     def link(exchanges) -> None:
@@ -103,15 +116,24 @@ class PeerExchange:
     def _stream(self):
         return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_timeout_ms(self, ms: int) -> None:
+        self._lib.check(self._lib.lib().frs_exchange_set_timeout_ms(self._h, int(ms)))
+
+    def status(self) -> None:
+        """Raises FrsError (FRS_E_TIMEOUT) once a peer failed to publish a batch in time."""
+        self._lib.check(self._lib.lib().frs_exchange_status(self._h))
+
     def push(self, local_packed: torch.Tensor) -> None:
+        """Stand-alone push of a block in the exchange's layout ([2, nq, k] dense for the shapes it was created with)."""
         assert local_packed.dtype == torch.int64 and tuple(local_packed.shape) == (2, self.nq, self.k) and local_packed.is_contiguous()
         self._lib.check(self._lib.lib().frs_exchange_push(self._h, self._C.c_void_p(local_packed.data_ptr()), self._stream()))
 
-    def wait_merge(self):
-        out_s = torch.empty((self.nq, self.k), dtype=torch.float32, device=self.device)
-        out_i = torch.empty((self.nq, self.k), dtype=torch.int64, device=self.device)
-        self._lib.check(self._lib.lib().frs_exchange_wait_merge(self._h, self._C.c_void_p(out_s.data_ptr()),
-                                                                self._C.c_void_p(out_i.data_ptr()), self._stream()))
+    def wait_merge(self, nq: Optional[int] = None, k: Optional[int] = None):
+        nq, k = int(nq or self.nq), int(k or self.k)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        self._lib.check(self._lib.lib().frs_exchange_wait_merge_n(self._h, nq, k, self._C.c_void_p(out_s.data_ptr()),
+                                                                  self._C.c_void_p(out_i.data_ptr()), self._stream()))
         return out_i, out_s
 
     def close(self) -> None:
@@ -123,15 +145,21 @@ class PeerExchange:
 class ShardedIndex:
     def __init__(self, local_index, rank: int, world: int, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 device: Optional[torch.device] = None, reserve_sms: int = 8, exchange: Optional[str] = None):
+                 device: Optional[torch.device] = None, reserve_sms: int = 8, exchange: Optional[str] = None,
+                 timeout_ms: Optional[int] = None):
         """local_index: a VectorIndex whose base is this shard's first global row (or any object
         when local_search/merge are injected).
 
-        reserve_sms: the scan kernel is persistent with one CTA per SM and all of shared memory, so a
-        collective kernel that is still resident when the next scan starts keeps scan CTAs waiting for an
-        SM — a static tile split then ends a whole "wave" late (measured on 8 B200, 1.25M rows per GPU:
-        scan 255 us instead of 151 us, 110k instead of 181k QPS).  With world > 1 the scan therefore
-        leaves `reserve_sms` SMs to the exchange (NCCL_MAX_NCHANNELS=1..2 keeps NCCL inside them)."""
+        exchange: "p2p" (default on CUDA) = stores into the peers' buffers over NVLink peer memory, fused into the
+        local merge kernel, flags + a bounded wait (csrc/exchange.cu); ONE exchange object (32 queries x 16) is
+        created here, collectively, and serves every batch.  "nccl" = one all-gather of the packed
+        (score, id) lists per batch (the form north_star names; also what the injectable CPU path under gloo
+        uses).  "auto" = p2p, falling back to nccl on every rank if CUDA IPC is unavailable on any.
+
+        reserve_sms (nccl form only): the scan kernel is persistent with one CTA per SM and all of shared memory,
+        so a collective kernel still resident when the next scan starts keeps scan CTAs waiting for an SM; the
+        scan then leaves `reserve_sms` SMs free.  The p2p pipelined form reserves SMs inside the library
+        (frs_index_set_pipeline_reserve)."""
         self.local = local_index
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device if device is not None else getattr(local_index, "device", torch.device("cpu"))
@@ -141,22 +169,27 @@ class ShardedIndex:
         self._slot = 0
         self._slot_free = [None, None]  # event: the side stream is done with this slot's buffers
         self._bufs = {}
-        # exchange step: "p2p" = writes into the peers' buffers over NVLink (PeerExchange), "nccl" = one all-gather.
-        # The injectable CPU path (gloo tests) and world 1 use the collective form.
         import os
 
-        # "auto" (default): the synchronous search() — the latency path a request sees — uses the push fused into
-        # the local merge kernel (8 GPUs, 10M rows: 109 k vs 86 k QPS host to host), the pipelined search_async()
-        # keeps the all-gather on its side stream, where it is hidden completely behind the next local pass
-        # (181 k vs 137 k QPS device-timed: the fused push sits on the main stream and lengthens the merge kernel).
-        cuda_path = self.world > 1 and merge is None and self.device.type == "cuda"
+        cuda_path = self.world > 1 and merge is None and local_search is None and self.device.type == "cuda"
         self.exchange = (exchange or os.environ.get("FRS_EXCHANGE") or "auto").lower()
         if self.exchange not in ("auto", "p2p", "nccl"):
             raise ValueError(f"exchange must be 'auto', 'p2p' or 'nccl', got {self.exchange!r}")
         if not cuda_path:
             self.exchange = "nccl"
-        self._peer = {}
-        if self.world > 1 and local_search is None and self.device.type == "cuda" and reserve_sms > 0:
+        self._peer: Optional[PeerExchange] = None
+        if self.exchange in ("auto", "p2p"):
+            try:
+                self._peer = PeerExchange(self.device, self.world, self.rank, group=self.group, timeout_ms=timeout_ms)
+                self.exchange = "p2p"
+            except RuntimeError as e:
+                if self.exchange != "auto":
+                    raise
+                import warnings
+
+                warnings.warn(f"{e}; using the NCCL all-gather exchange")
+                self.exchange = "nccl"
+        if self.exchange == "nccl" and cuda_path and reserve_sms > 0:
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             if sms > 2 * reserve_sms and hasattr(local_index, "set_scan_grid"):
                 local_index.set_scan_grid(sms - reserve_sms)
@@ -182,23 +215,6 @@ class ShardedIndex:
             self._bufs[key] = (loc, gat)
         return self._bufs[key]
 
-    def _peer_exchange(self, nq: int, k: int) -> Optional["PeerExchange"]:
-        """Collective on first use: every rank creates and connects it.  In "auto" mode a set-up that fails on any
-        rank (no CUDA IPC) switches every rank to the all-gather form — both are GPU paths; "p2p" raises."""
-        key = (nq, k)
-        if key not in self._peer:
-            try:
-                self._peer[key] = PeerExchange(self.device, self.world, self.rank, nq, k, group=self.group)
-            except RuntimeError as e:
-                if self.exchange != "auto":
-                    raise
-                import warnings
-
-                warnings.warn(f"{e}; using the NCCL all-gather exchange")
-                self.exchange = "nccl"
-                return None
-        return self._peer[key]
-
     def _exchange_and_merge(self, loc: torch.Tensor, gat: torch.Tensor, k: int):
         if self.world > 1:
             # output viewed as the concatenation of the per-rank inputs along dim 0 (what gloo expects;
@@ -216,24 +232,28 @@ class ShardedIndex:
         """Synchronous-in-stream sharded search; every rank must call it with the same queries.
         Returns (ids int64 [nq,k] global, scores float32 [nq,k]) on every rank."""
         q, qc, qm = self._prep(queries, q_code, q_mask)
-        if self._side is not None:  # after pipelined calls: their exchanges come first (sequence numbers, slots)
-            torch.cuda.current_stream(self.device).wait_stream(self._side)
-        ex = self._peer_exchange(q.shape[0], k) if self.exchange in ("p2p", "auto") else None
-        if ex is not None:
+        if self._peer is not None:
+            # after pipelined calls: their exchanges come first (sequence numbers, gather slots)
+            self.local.wait(-1)
             # the local merge kernel writes the shard's top-k into every peer's gather buffer itself
-            self.local.search_push(q, qc, qm, k, ex)
-            return ex.wait_merge()
+            self.local.search_push(q, qc, qm, k, self._peer)
+            return self._peer.wait_merge(q.shape[0], k)
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
         loc, gat = self._buffers(q.shape[0], k, 0)
         self._local_pass(q, qc, qm, k, loc)
         return self._exchange_and_merge(loc, gat, k)
 
-    def search_async(self, queries, q_code, q_mask, k: int = 15) -> PendingSearch:
-        """Pipelined variant (CUDA only): the exchange and final merge run on a side stream so the
-        next call's local pass overlaps them.  Alternates between two buffer sets."""
+    def search_async(self, queries, q_code, q_mask, k: int = 15):
+        """Pipelined variant (CUDA only).  p2p: one library call; the prep of the next batch and the merge + push +
+        wait + cross-shard merge of the previous one overlap this batch's scan on the index's internal streams.
+        nccl: the all-gather and final merge run on a side stream.  Returns an object with .wait() -> (ids, scores)."""
         assert self.device.type == "cuda", "search_async needs CUDA streams"
+        q, qc, qm = self._prep(queries, q_code, q_mask)
+        if self._peer is not None:
+            return self.local.search_async(q, qc, qm, k, exchange=self._peer)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
-        q, qc, qm = self._prep(queries, q_code, q_mask)
         main = torch.cuda.current_stream(self.device)
         slot = self._slot
         self._slot ^= 1
@@ -244,30 +264,40 @@ class ShardedIndex:
         self._local_pass(q, qc, qm, k, loc)
         done_local = torch.cuda.Event()
         done_local.record(main)
-        # "p2p": the stand-alone push of the finished block + wait + merge, all on the side stream (the push of
-        # batch t + 1 is stream-ordered behind this rank's merge of batch t, the d = 1 case of the slot rule in
-        # csrc/scan.cuh).  The push FUSED into the merge kernel would sit on the caller's stream in front of the
-        # next scan (8 GPUs: 137 k against 181 k QPS), so the pipelined form does not use it.
-        ex = self._peer_exchange(q.shape[0], k) if self.exchange == "p2p" else None
         with torch.cuda.stream(self._side):
             self._side.wait_event(done_local)
-            if ex is not None:
-                ex.push(loc)
-                ids, scores = ex.wait_merge()
-            else:
-                ids, scores = self._exchange_and_merge(loc, gat, k)
+            ids, scores = self._exchange_and_merge(loc, gat, k)
             ready = torch.cuda.Event()
             ready.record(self._side)
         self._slot_free[slot] = ready
         return PendingSearch(ids, scores, ready)
 
+    def drain(self) -> None:
+        """The current stream waits for every pipelined search issued so far."""
+        if self._peer is not None:
+            self.local.wait(-1)
+        elif self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+
+    # -- host buffers in / out (what a request handler calls) -------------------------------------------
+    def submit_host(self, queries, q_code, q_mask, k: int = 15) -> int:
+        """numpy in; returns a ticket for collect_host.  One pinned H2D + one D2H copy per batch inside the library,
+        overlapping the neighbouring batches (up to 4 in flight).  Every rank submits the same batches in order."""
+        if self._peer is None:
+            raise RuntimeError("submit_host needs the peer-memory exchange (exchange='p2p')")
+        return self.local.submit_host(queries, q_code, q_mask, k, exchange=self._peer)
+
+    def collect_host(self, ticket: int):
+        return self.local.collect_host(ticket, exchange=self._peer)
+
     def close(self) -> None:
-        """Releases the peer-memory exchanges (IPC mappings, gather buffers).  The local index stays open."""
+        """Releases the peer-memory exchange (IPC mappings, gather buffers).  The local index stays open."""
         if self._side is not None:
             self._side.synchronize()
-        for ex in self._peer.values():
-            ex.close()
-        self._peer = {}
+        if self._peer is not None:
+            self.local.sync(-1)
+            self._peer.close()
+            self._peer = None
 
     def _prep(self, queries, q_code, q_mask):
         q = torch.as_tensor(queries).to(device=self.device, dtype=torch.float32).contiguous()

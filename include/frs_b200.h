@@ -37,13 +37,14 @@
 extern "C" {
 #endif
 
-#define FRS_VERSION 100 /* 0.1.0 */
+#define FRS_VERSION 200 /* 0.2.0 */
 
 #define FRS_OK 0
 #define FRS_E_INVALID (-1) /* bad argument                               */
 #define FRS_E_CUDA (-2)    /* CUDA runtime / driver error                */
 #define FRS_E_CAPACITY (-3) /* index full                                */
 #define FRS_E_STATE (-4)   /* call not valid in this state               */
+#define FRS_E_TIMEOUT (-5) /* a peer rank of a sharded search did not answer within the exchange's time-out */
 
 #define FRS_DIM 384      /* VectorParams(size=384)  ingest.py:89-95        */
 #define FRS_MAX_BATCH 32 /* MAX_BATCH_SIZE          main2.py:51            */
@@ -84,11 +85,15 @@ int frs_index_destroy(frs_index* idx);
 int64_t frs_index_size(const frs_index* idx);
 int64_t frs_index_capacity(const frs_index* idx);
 int frs_index_dtype(const frs_index* idx);
+int frs_index_device(const frs_index* idx);
 /* first global row id of this shard (ids returned by search = base + local row) */
 int frs_index_set_base(frs_index* idx, int64_t base);
 /* number of CTAs of the scan kernel (0 = one per SM).  Results do not depend on it; exposed so
  * the tests can prove that. */
 int frs_index_set_scan_grid(frs_index* idx, int grid);
+/* SMs the persistent scan kernel leaves free in the PIPELINED entry points (default 4), so that the neighbouring
+ * batches' prepare / merge / exchange kernels can run beside it.  Results do not depend on it. */
+int frs_index_set_pipeline_reserve(frs_index* idx, int sms);
 
 /* qdrant.upsert(points)  ingest.py:171-175: L2-normalise (cosine collection),
  * convert to the storage dtype and append.  vecs: [n, 384] fp32, codes: [n]. */
@@ -96,7 +101,9 @@ int frs_index_add(frs_index* idx, const float* dev_vecs, const uint32_t* dev_cod
                   void* stream);
 int frs_index_add_host(frs_index* idx, const float* host_vecs, const uint32_t* host_codes,
                        int64_t n);
-/* overwrite rows [row0, row0+n) (idempotent upsert on an existing id) */
+/* overwrite rows [row0, row0+n) (idempotent upsert on an existing id); dev_codes == NULL keeps the stored codes.
+ * Writes and searches may be issued concurrently from different threads / streams (the reference serves queries
+ * from 25 threads while ingest.py upserts, main2.py:52-53): a search never reads a half-written row. */
 int frs_index_set_rows(frs_index* idx, int64_t row0, const float* dev_vecs,
                        const uint32_t* dev_codes, int64_t n, void* stream);
 /* overwrite payload codes only (tombstoning) */
@@ -133,6 +140,34 @@ int frs_index_search_host(frs_index* idx, const float* host_queries, const uint3
                           const uint32_t* host_q_mask, int nq, int k, float* host_out_scores,
                           int64_t* host_out_ids);
 
+/* Pipelined forms.  The search is three kernels (prepare queries -> scan -> merge); these entry points run them
+ * on three internal streams of the index, so that consecutive calls overlap: the preparation of batch i+1 and
+ * the merge (+ cross-shard exchange) of batch i-1 run while batch i is being scanned, and the scan kernels run
+ * back to back.  This is how the 32-query dynamic batches of main2.py:281-295 are meant to be fed.
+ *
+ *   frs_index_search_async   device buffers.  Inputs are read in `in_stream` order; results are complete once
+ *                            the ticket has been waited for: frs_index_wait (makes a stream wait, ticket -1 =
+ *                            everything submitted so far) or frs_index_sync (blocks the host).  A ticket stays
+ *                            valid for the next 15 submissions.  `ex` != NULL: sharded search, the shard's local
+ *                            top-k is exchanged with the other ranks (see frs_exchange_*) and the outputs are the
+ *                            global top-k; every rank submits the same batches in the same order.
+ *   frs_index_search_host_submit / _collect
+ *                            host buffers: one pinned H2D copy and one D2H copy per batch, both overlapping the
+ *                            neighbouring batches' scans.  Up to 4 batches in flight per index (a 5th submit
+ *                            blocks until a collect).  frs_index_search_host == submit + collect; it may be
+ *                            called from many threads at once (main2.py:52-53: 25 concurrent requests), each call
+ *                            taking its own staging slot. */
+int frs_index_search_async(frs_index* idx, frs_exchange* ex, const float* dev_queries, const uint32_t* dev_q_code,
+                           const uint32_t* dev_q_mask, int nq, int k, float* dev_out_scores,
+                           int64_t* dev_out_ids, void* in_stream, int* ticket);
+int frs_index_wait(frs_index* idx, int ticket, void* stream);
+int frs_index_sync(frs_index* idx, int ticket);
+int frs_index_search_host_submit(frs_index* idx, frs_exchange* ex, const float* host_queries,
+                                 const uint32_t* host_q_code, const uint32_t* host_q_mask, int nq, int k,
+                                 int* ticket);
+int frs_index_search_host_collect(frs_index* idx, frs_exchange* ex, int ticket, float* host_out_scores,
+                                  int64_t* host_out_ids);
+
 /* Ticker-segmented search: the same exact search restricted to the listed 128-row tiles
  * (tile t = rows [128 t, 128 t + 128); ascending, unique).  The caller guarantees that every row that
  * can match ANY query's predicate lies in a listed tile — ingest is per ticker (ingest.py:109-177), so
@@ -156,13 +191,19 @@ int frs_merge_shards_packed(int device, const int64_t* dev_packed, int n_shards,
                             float* dev_out_scores, int64_t* dev_out_ids, void* stream);
 
 /* Cross-shard exchange over NVLink peer memory (replaces the all-gather of the sharded search; the reference
- * has one Qdrant server and no counterpart, main.py:215-239).  Every rank creates an exchange, the 128-byte
- * handles (two CUDA IPC handles) are all-gathered by the host, frs_exchange_connect maps the peers' buffers.
- * Per batch: frs_exchange_push writes this rank's [2][nq][k] block (as left by frs_index_search_local, nq/k as
- * created) into every peer's gather buffer and publishes a sequence number; frs_exchange_wait_merge waits for
- * all ranks' pushes of that sequence number and merges to the global top-k.  Both are asynchronous on `stream`;
- * every rank must call them once per batch, in the same order.  frs_exchange_connect_local links several
- * exchanges of ONE process by pointer (several shards on one GPU, tests). */
+ * has one Qdrant server and no counterpart, main.py:215-239).  One process per GPU: every rank creates an exchange
+ * (nq_max <= 32, k_max <= 16: ONE exchange serves every batch size and limit up to those), the 128-byte handles
+ * (two CUDA IPC handles) are all-gathered by the host, frs_exchange_connect maps the peers' buffers.
+ * Per batch: the local pass pushes this rank's exact top-k into every peer's gather buffer and publishes a
+ * sequence number (fused into the merge kernel: frs_index_search_push / frs_index_search_async /
+ * frs_index_search_host_submit with `ex`; frs_exchange_push is the stand-alone form for a block in the exchange's
+ * layout [2][nq_max][k_max], entry (q, r) of a plane at q * k + r); frs_exchange_wait_merge[_n] waits for all
+ * ranks' pushes of that sequence number and merges to the global top-k.  Every rank issues the same batches
+ * (same nq, k) in the same order.  frs_exchange_connect_local links several exchanges of ONE process by pointer
+ * (several shards on one GPU, or one shard per GPU with peer access).
+ * A peer that does not publish within the time-out (default 30 s) poisons the exchange: that batch and all later
+ * ones return empty results, the host-buffer entry points and frs_exchange_status return FRS_E_TIMEOUT, and the
+ * exchange has to be destroyed and re-created on every rank.  Nothing traps; the shard stays resident. */
 int frs_exchange_create(int device, int world, int rank, int nq_max, int k_max, frs_exchange** out);
 int frs_exchange_destroy(frs_exchange* ex);
 int frs_exchange_handle(frs_exchange* ex, uint8_t* out128);
@@ -170,10 +211,48 @@ int frs_exchange_connect(frs_exchange* ex, const uint8_t* handles_world_by_128);
 int frs_exchange_connect_local(frs_exchange* ex, frs_exchange* const* peers);
 int frs_exchange_push(frs_exchange* ex, const int64_t* dev_local_packed, void* stream);
 int frs_exchange_wait_merge(frs_exchange* ex, float* dev_out_scores, int64_t* dev_out_ids, void* stream);
+int frs_exchange_wait_merge_n(frs_exchange* ex, int nq, int k, float* dev_out_scores, int64_t* dev_out_ids,
+                              void* stream);
+int frs_exchange_set_timeout_ms(frs_exchange* ex, int64_t ms);
+int frs_exchange_status(frs_exchange* ex);
 /* the local pass with the push FUSED into its merge kernel (one CTA per query writes its k results into every
  * peer's gather buffer, the last CTA publishes the flags): replaces frs_index_search_local + frs_exchange_push */
 int frs_index_search_push(frs_index* idx, const float* dev_queries, const uint32_t* dev_q_code,
                           const uint32_t* dev_q_mask, int nq, int k, frs_exchange* ex, void* stream);
+
+/* ---- one process, several GPUs ------------------------------------------
+ * get_qdrant() hands the reference ONE client object inside ONE server process (main.py:92-95,
+ * main2.py:104-108) and retrieve_from_qdrant calls it from a thread pool (main.py:215-239, main2.py:160-163):
+ * frs_sharded is that object for a store spread over the GPUs of a box.  Rows are placed block-cyclically
+ * (blocks of frs_sharded_block_rows() rows: global row g -> shard (g / B) % n), ids are global row numbers in
+ * insertion order exactly as for a single frs_index, and a search returns the same ids and scores as one
+ * frs_index holding all rows.  Every shard's merge kernel writes its exact top-k into the collecting GPU's
+ * buffer over NVLink peer memory; CUDA events order the GPUs (no collective library, no flag polling).
+ * search_host may be called from many threads; submit / collect keep up to 4 batches in flight. */
+typedef struct frs_sharded frs_sharded;
+int frs_sharded_create(int n_devices, const int* devices /* NULL = 0..n-1 */, int dim, int64_t capacity_total,
+                       int dtype, frs_sharded** out);
+int frs_sharded_destroy(frs_sharded* sh);
+int frs_sharded_n_shards(const frs_sharded* sh);
+int64_t frs_sharded_size(const frs_sharded* sh);
+int64_t frs_sharded_capacity(const frs_sharded* sh);
+int64_t frs_sharded_block_rows(const frs_sharded* sh);
+/* borrow shard s (device-side fill through frs_index_add in block order, diagnostics); owned by `sh` */
+frs_index* frs_sharded_shard(frs_sharded* sh, int s);
+int frs_sharded_set_size(frs_sharded* sh, int64_t n);
+int frs_sharded_add_host(frs_sharded* sh, const float* host_vecs, const uint32_t* host_codes, int64_t n);
+/* overwrite global rows [row0, row0+n): vectors (+ codes), or codes only when host_vecs == NULL */
+int frs_sharded_set_rows_host(frs_sharded* sh, int64_t row0, const float* host_vecs, const uint32_t* host_codes,
+                              int64_t n);
+int frs_sharded_read_rows_host(frs_sharded* sh, int64_t row0, int64_t n, float* host_out);
+int frs_sharded_export_raw(frs_sharded* sh, int64_t row0, int64_t n, void* host_rows, uint32_t* host_codes);
+int frs_sharded_import_raw(frs_sharded* sh, const void* host_rows, const uint32_t* host_codes, int64_t n);
+int frs_sharded_search_host(frs_sharded* sh, const float* host_queries, const uint32_t* host_q_code,
+                            const uint32_t* host_q_mask, int nq, int k, float* host_out_scores,
+                            int64_t* host_out_ids);
+int frs_sharded_search_host_submit(frs_sharded* sh, const float* host_queries, const uint32_t* host_q_code,
+                                   const uint32_t* host_q_mask, int nq, int k, int* ticket);
+int frs_sharded_search_host_collect(frs_sharded* sh, int ticket, float* host_out_scores, int64_t* host_out_ids);
 
 /* the prepared (normalised, storage-dtype-rounded) queries of the last search,
  * widened to fp32: what the scores are dot products with.  [FRS_MAX_BATCH, 384] */
@@ -191,8 +270,14 @@ int frs_index_last_stats(frs_index* idx, int64_t* host_out6);
  * kernel of a search (prep, scan, merge); mode 2: additionally the scan kernel stamps a per-CTA
  * timeline.  read_profile synchronises and returns {searches, prep ms, scan ms, merge ms} summed
  * over the searches recorded since the last read (at most the last 256). */
+/* mode 3 (bracket): only ONE event before the first scan kernel and one after the latest, on the stream the scan
+ * runs on: read_profile[_ex] then returns {scans, 0, ms from the first scan's start to the last scan's end, ...} —
+ * the scan's average launch duration (gaps between launches included) with no events between a step's kernels. */
 int frs_index_set_profiling(frs_index* idx, int mode);
 int frs_index_read_profile(frs_index* idx, double* host_out4);
+/* {searches, prep ms, scan ms, merge ms, exchange ms (cross-shard wait + merge), scan-stream gap ms (end of one
+ * scan kernel to the start of the next, summed), span ms (first prep start to last search end), 0} */
+int frs_index_read_profile_ex(frs_index* idx, double* host_out8);
 /* [n_ctas, 16] globaltimer ns: start, first slab landed, last MMA issued, first tile consumed,
  * last tile consumed, exit, then stamps of the first rare-path invocation (diagnostics) */
 int frs_index_read_timeline(frs_index* idx, uint64_t* host_out, int n_ctas);

@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# Several tests link the exchanges of 3 shards inside ONE process; with 4 streams per index that is more streams than
+# the default 8 hardware queues, and a spinning exchange-wait kernel would then sit in front of the very kernel it
+# waits for (false dependency through a shared queue).  One rank per process (the product form) is not affected.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -33,7 +33,7 @@ def test_ctypes_table_mirrors_header():
 
 def test_version_and_error_string():
     lib = _lib.lib()
-    assert lib.frs_version() == 100
+    assert lib.frs_version() == 200
     assert isinstance(lib.frs_last_error(), bytes)
 
 

@@ -47,10 +47,10 @@ class OracleIndex:
         return torch.from_numpy(ids.astype(np.int64)), torch.from_numpy(sc.astype(np.float32))
 
     def set_rows(self, row0, vecs, codes=None):
-        v = so.store_rows(vecs.cpu().numpy(), "f32")
+        v = so.store_rows(np.asarray(vecs, dtype=np.float32), "f32")
         self.rows[row0:row0 + len(v)] = v
         if codes is not None:
-            self.codes[row0:row0 + len(v)] = codes.cpu().numpy().astype(np.int64).astype(np.uint32)
+            self.codes[row0:row0 + len(v)] = np.asarray(codes).astype(np.int64).astype(np.uint32)
 
     def export_raw(self, row0=0, n=None):
         n = len(self.rows) - row0 if n is None else n
