@@ -507,6 +507,8 @@ def run_ours(args):
         ix.set_scan_grid(int(os.environ["FRS_SCAN_GRID"]))
     if os.environ.get("FRS_PIPE_RESERVE"):
         ix.set_pipeline_reserve(int(os.environ["FRS_PIPE_RESERVE"]))
+    if os.environ.get("FRS_SCAN_STREAMS"):
+        ix.set_scan_streams(int(os.environ["FRS_SCAN_STREAMS"]))
     hq, dq = device_queries(cx, args.queries)
     tiles_dev, n_tiles_total = None, (length + 127) // 128
     if grouped:
@@ -593,7 +595,7 @@ def run_ours(args):
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
-        cb = cpu_baseline() if cx.world == 1 else None
+        cb = cpu_baseline() if cx.world == 1 and not os.environ.get("FRS_BENCH_NO_CPU") else None
         cfg = workload_config(cx.world, args.queries)
         if grouped:
             cfg["layout"] = (f"rows grouped by ticker (ingest order); the batch's {int(np.unique(hq[1]).size)} tickers occupy "

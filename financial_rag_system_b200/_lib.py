@@ -42,6 +42,7 @@ PROTOTYPES = {
     "frs_index_set_base": (_int, [_vp, _i64]),
     "frs_index_set_scan_grid": (_int, [_vp, _int]),
     "frs_index_set_pipeline_reserve": (_int, [_vp, _int]),
+    "frs_index_set_scan_streams": (_int, [_vp, _int]),
     "frs_index_add": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "frs_index_add_host": (_int, [_vp, _vp, _vp, _i64]),
     "frs_index_set_rows": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),

@@ -159,7 +159,7 @@ static void free_index(frs_index* ix) {
     if (ix->job_done[i]) cudaEventDestroy(ix->job_done[i]);
   }
   if (ix->rows_ready) cudaEventDestroy(ix->rows_ready);
-  for (cudaStream_t s : {ix->s_prep, ix->s_scan, ix->s_merge, ix->stream})
+  for (cudaStream_t s : {ix->s_prep, ix->s_scan[0], ix->s_scan[1], ix->s_merge, ix->stream})
     if (s) cudaStreamDestroy(s);
   delete ix;
 }
@@ -214,7 +214,8 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
     IX_TRY(cudaMalloc(&w.stats, kStatSlots * 8));
     IX_TRY(cudaMemset(w.stats, 0, kStatSlots * 8));
     IX_TRY(cudaMalloc(&w.gmax, (size_t)kNQ * kGmaxPad * 4));
-    IX_TRY(cudaMalloc(&w.gsample, (size_t)kNQ * kSampleBlocks * 4));
+    IX_TRY(cudaMalloc(&w.gsample, (size_t)kSampleFloats * 4));
+    IX_TRY(cudaMemset(w.gsample, 0, (size_t)kSampleFloats * 4));  // (the block counter starts at 0 and resets itself)
     IX_TRY(cudaMalloc(&w.spill, merge_spill_bytes()));
     IX_TRY(cudaEventCreateWithFlags(&w.free, cudaEventDisableTiming));
   }
@@ -234,12 +235,13 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
     IX_TRY(cudaEventCreateWithFlags(&ix->job_done[i], cudaEventDisableTiming));
   }
   IX_TRY(cudaEventCreateWithFlags(&ix->rows_ready, cudaEventDisableTiming));
-  // the scan stream outranks the others: when a scan and a prep / merge are both ready, the scan's CTAs go first
+  // prep / merge / exchange kernels are short and gate the next scan: when an SM frees up they go first
   int prio_lo = 0, prio_hi = 0;
   IX_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  IX_TRY(cudaStreamCreateWithPriority(&ix->s_prep, cudaStreamNonBlocking, prio_lo));
-  IX_TRY(cudaStreamCreateWithPriority(&ix->s_scan, cudaStreamNonBlocking, prio_hi));
-  IX_TRY(cudaStreamCreateWithPriority(&ix->s_merge, cudaStreamNonBlocking, prio_lo));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_prep, cudaStreamNonBlocking, prio_hi));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_scan[0], cudaStreamNonBlocking, prio_lo));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_scan[1], cudaStreamNonBlocking, prio_lo));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_merge, cudaStreamNonBlocking, prio_hi));
   IX_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   IX_TRY(preload_search_kernels());
   IX_TRY(cudaDeviceSynchronize());  // the memsets above ran on the legacy stream; the internal streams do not sync with it
@@ -281,8 +283,14 @@ extern "C" int frs_index_set_scan_grid(frs_index* idx, int grid) {
 // next to one of its CTAs.  The pipelined entry points therefore run it on (SMs - reserve) CTAs: the prep kernel of
 // the next batch and the merge / exchange kernels of the previous one run on the SMs left over.
 extern "C" int frs_index_set_pipeline_reserve(frs_index* idx, int sms) {
-  if (!idx || sms < 0 || sms > 64) return set_err(FRS_E_INVALID, "bad argument");
+  if (!idx || sms < -1 || sms > 64) return set_err(FRS_E_INVALID, "bad argument");
   idx->pipe_reserve = sms;
+  return FRS_OK;
+}
+// experiment knob: 1 = every scan on one stream (launches strictly one after the other), 2 = alternate (default)
+extern "C" int frs_index_set_scan_streams(frs_index* idx, int n) {
+  if (!idx || n < 1 || n > 2) return set_err(FRS_E_INVALID, "bad argument");
+  idx->scan_streams = n;
   return FRS_OK;
 }
 extern "C" void* frs_index_rows_ptr(frs_index* idx) { return idx ? idx->rows : nullptr; }
@@ -464,6 +472,13 @@ extern "C" int frs_index_import_raw(frs_index* idx, const void* host_rows, const
 // search
 // ---------------------------------------------------------------------------------------------
 static int scan_grid(const frs_index* ix, uint32_t num_tiles, int reserve = 0) {
+  if (reserve < 0) {
+    // auto: the prep and merge kernels of the neighbouring batches must finish inside one scan period on the SMs the
+    // scan leaves free, so short scans (small shards) leave more (measured on B200: 10M rows/GPU best with 4,
+    // 1.25M rows/GPU with 12)
+    const uint32_t per_sm = num_tiles / (uint32_t)(ix->sm_count > 0 ? ix->sm_count : 1);
+    reserve = per_sm >= 384 ? 4 : per_sm >= 160 ? 8 : 12;
+  }
   int g = ix->grid_override > 0 ? ix->grid_override : ix->sm_count - (ix->sm_count > 4 * reserve ? reserve : 0);
   if (g > ix->max_parts) g = ix->max_parts;
   if ((uint32_t)g > num_tiles) g = (int)num_tiles;
@@ -491,7 +506,7 @@ int search_enqueue(frs_index* ix, const SearchArgs& a, const SearchLaunch& L) {
   int launches = 0;
   if (pev) CU_TRY(cudaEventRecord(pev[0], L.prep));
   CU_TRY(launch_prep_queries(f32, a.q, a.code, a.mask, a.nq, w.qop, w.qrec, w.qcode, w.qmask, w.stats, w.gmax,
-                             w.gsample, ix->rows, ix->codes, (uint32_t)ix->size, L.prep));
+                             w.gsample, ix->rows, ix->codes, (uint32_t)ix->size, a.k, eps, L.prep));
   launches++;
   if (pev) CU_TRY(cudaEventRecord(pev[1], L.prep));
   if (L.scan != L.prep) {
@@ -530,7 +545,7 @@ int search_enqueue(frs_index* ix, const SearchArgs& a, const SearchLaunch& L) {
     sp.part_cnt = w.part_cnt;
     sp.dbg_scores = nullptr;
     sp.gmax = w.gmax;
-    sp.gsample = w.gsample;
+    sp.tau0 = w.gsample + kSampleTau0;
     sp.stats = w.stats;
     sp.timeline = ix->prof_mode == 2 ? ix->timeline : nullptr;
     if (sp.timeline) CU_TRY(cudaMemsetAsync(ix->timeline, 0, (size_t)kGmaxPad * 16 * 8, L.scan));
@@ -588,7 +603,7 @@ int pipelined_begin(frs_index* ix, bool has_in, cudaStream_t in_stream, int* slo
     CU_TRY(cudaStreamWaitEvent(ix->s_prep, ix->job_in[s], 0));
   }
   L->prep = ix->s_prep;
-  L->scan = ix->s_scan;
+  L->scan = ix->s_scan[ix->scan_streams > 1 ? (int)((ix->jobs - 1) & 1) : 0];
   L->merge = ix->s_merge;
   L->ev_prep = ix->job_prep[s];
   L->ev_scan = ix->job_scan[s];
@@ -937,7 +952,7 @@ extern "C" int frs_index_debug_scores(frs_index* idx, const float* dev_queries, 
   CU_TRY(cudaStreamWaitEvent(st, idx->rows_ready, 0));
   CU_TRY(cudaMemsetAsync(w.qcode, 0, kNQ * 4, st));  // all-zero (code, mask): every row passes the predicate
   CU_TRY(launch_prep_queries(f32, dev_queries, w.qcode, w.qcode, nq, w.qop, w.qrec, w.qcode, w.qmask, w.stats, w.gmax,
-                             w.gsample, idx->rows, idx->codes, (uint32_t)idx->size, st));
+                             w.gsample, idx->rows, idx->codes, (uint32_t)idx->size, 1, 0.f, st));
   const uint32_t n = (uint32_t)idx->size;
   const uint32_t num_tiles = (n + kTileM - 1) / kTileM;
   const int grid = scan_grid(idx, num_tiles);
@@ -955,7 +970,7 @@ extern "C" int frs_index_debug_scores(frs_index* idx, const float* dev_queries, 
     sp.eps = 0.f;
     sp.dbg_scores = dev_out;
     sp.gmax = w.gmax;
-    sp.gsample = w.gsample;
+    sp.tau0 = w.gsample + kSampleTau0;
     sp.stats = w.stats;
     CU_TRY(launch_scan(f32, true, grid, idx->tmap_rows, w.tmap_q, sp, st));
   }

@@ -86,7 +86,7 @@ struct frs_index {
   uint32_t id_block = 0, id_shards = 1, id_shard = 0;  // block-cyclic id mapping (sharded.cu), 0 = base + row
   int sm_count = 0;
   int grid_override = 0;
-  int pipe_reserve = 4;  // see frs_index_set_pipeline_reserve
+  int pipe_reserve = -1;  // see frs_index_set_pipeline_reserve (-1 = chosen from the shard size)
   void* rows = nullptr;
   uint32_t* codes = nullptr;
   CUtensorMap tmap_rows;
@@ -95,7 +95,11 @@ struct frs_index {
   int ws_last = 0;
   int max_parts = 0;
   // internal streams of the pipelined form + the write path
-  cudaStream_t s_prep = nullptr, s_scan = nullptr, s_merge = nullptr;
+  // Consecutive scans alternate between TWO streams: they are independent kernels (separate workspaces), so the
+  // CTAs of scan i+1 start on SMs as the CTAs of scan i leave them — the ramp of one launch fills the tail of the
+  // previous one instead of both being bubbles (at 1.25M rows per GPU they were ~15 % of a launch).
+  cudaStream_t s_prep = nullptr, s_scan[2] = {nullptr, nullptr}, s_merge = nullptr;
+  int scan_streams = 2;
   cudaStream_t stream = nullptr;  // host-call write path (add_host, read_rows_host)
   cudaEvent_t job_in[frs::kJobRing], job_prep[frs::kJobRing], job_scan[frs::kJobRing], job_done[frs::kJobRing];
   uint64_t jobs = 0;

@@ -449,7 +449,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
   if (threadIdx.x < kNQ) {
     const int t = threadIdx.x;
     cnt[t] = 0;
-    taua[t] = t < p.nq ? -INFINITY : INFINITY;  // padded queries never pass
+    // padded queries never pass; live ones start from the prep kernel's bootstrap threshold (-inf when it found none)
+    taua[t] = t < p.nq ? (DUMP ? -INFINITY : __ldcg(p.tau0 + t)) : INFINITY;
     qcode[t] = t < p.nq ? p.qcode[t] : 0u;
     qmask[t] = t < p.nq ? p.qmask[t] : 0u;
     lmax[t] = f32_ordered(-INFINITY);
@@ -549,27 +550,6 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant
       const uint32_t r = FRS_TILE(l) * kTileM + lg * 32 + lane;
       return r < p.n ? __ldg(p.codes + r) : 0xFFFFFFFFu;
     };
-    if constexpr (!DUMP) {
-      // Bootstrap thresholds from the prep kernel's sample (lane = query): the k-th largest X of
-      // the sample blocks' best fp32 scores means k distinct rows with exact score >= X - eps_s
-      // exist, i.e. with pre-filter score >= X - eps_s - eps; rows under that minus 2*eps are out.
-      if (e.ew == 0) {
-        float t[kMaxK];
-        topk_init(t, p.k);
-#pragma unroll 1
-        for (int b0 = 0; b0 < kSampleBlocks; b0 += 32) {
-          float v[32];
-#pragma unroll
-          for (int b = 0; b < 32; ++b) v[b] = __ldcg(p.gsample + (b0 + b) * kNQ + lane);
-#pragma unroll
-          for (int b = 0; b < 32; ++b) topk_insert(t, v[b]);
-        }
-        const float kth = topk_kth(t);
-        if ((int)lane < p.nq && kth > -INFINITY)
-          atomic_max_f32(&taua[lane], __fsub_rd(__fsub_rd(kth, kEpsSample), 3.0f * p.eps));
-      }
-      named_bar_sync(1, kEpiThreads);
-    }
     uint32_t code_a = load_code(0);
     uint32_t code_b = load_code(1);
     uint32_t code_c = load_code(2);
@@ -1020,47 +1000,53 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// Query preparation + bootstrap sample.  kSampleBlocks blocks of 32 warps.  Every block normalises
-// the 32 query slots (one warp per slot; slots >= nq are zero) into shared memory; block 0 also writes
-// the MMA operand, the fp32 record copy, the predicate copies and resets the per-search tables.
-// Each block then scores kSampleRows sampled rows against all queries in fp32 and publishes its best
-// matching score per query: k distinct rows that good are known to exist before the scan starts, so
-// its first tiles do not have to accept everything.  The sampled rows are fetched (one DRAM latency,
-// overlapped with the normalisation) into shared memory; warp w scores half of row w/2, lane = query.
+// Query preparation + bootstrap sample.  kSampleBlocks blocks of 32 warps.  Every block normalises the 32 query
+// slots (one warp per slot; slots >= nq are zero) into shared memory; block 0 also writes the MMA operand, the
+// fp32 record copy, the predicate copies and resets the per-search tables.  Each block then scores kSampleRows
+// sampled rows (a stride over the whole store) against all queries in fp32 and publishes, per group of 16 rows, the
+// best MATCHING score per query; the last block to finish turns the 64 group maxima into the scan's starting thresholds:
+//   the k-th largest X of the block maxima belongs to k distinct rows with exact score >= X - eps_s, i.e. with
+//   pre-filter score >= X - eps_s - eps, so rows under X - eps_s - 3 eps can never reach the top-k.
+// The scan kernel starts from tau0 instead of accepting everything, and reads 32 floats instead of ranking the
+// sample itself on its ramp.  (A 4096-row sample halves the scan's list appends but does not shorten the launch —
+// its CTAs are HBM-bound from the first tiles on — while the longer prep kernel, squeezed onto the few SMs a running
+// scan leaves free, became the pipeline's bottleneck at 1.25M rows per GPU: measured, reverted.)
 constexpr int kQsStride = kDim + 1;  // +1: lanes read different queries at the same element
-constexpr int kPrepRowElems = kSampleRows * kDim / (32 * kNQ);  // row elements fetched per thread (6)
 constexpr size_t kPrepSmem = ((size_t)kNQ * kQsStride + (size_t)kSampleRows * kDim + 32 * 32) * sizeof(float);
 template <bool F32>
 __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
     const float* __restrict__ q, const uint32_t* __restrict__ code, const uint32_t* __restrict__ mask, int nq,
     void* __restrict__ qop, float* __restrict__ qrec, uint32_t* __restrict__ qcode, uint32_t* __restrict__ qmask,
     unsigned long long* stats, float* __restrict__ gmax, float* __restrict__ gsample,
-    const void* __restrict__ rows, const uint32_t* __restrict__ codes, uint32_t n) {
-  static_assert(kSampleRows * 2 == 32, "scoring maps warp w to (row w/2, half w%2)");
-  static_assert(kSampleRows * kDim % (32 * kNQ) == 0, "row elements must split evenly over the block");
+    const void* __restrict__ rows, const uint32_t* __restrict__ codes, uint32_t n, int k, float eps) {
+  static_assert(kSampleRows * 2 % 32 == 0, "scoring maps (row, half) pairs to the 32 warps");
+  static_assert(kSampleBlocks == 64, "the final selection holds two group maxima per lane");
+  static_assert(kSampleGroupRows == 16 && kSampleRows / kSampleGroupRows == 4, "a CTA scores 4 groups of 16 rows");
+  constexpr int kGroups = kSampleRows / kSampleGroupRows;
   extern __shared__ __align__(16) float psm[];
   float* rs = psm;                              // [kSampleRows][kDim] sampled rows widened to fp32
   float* qs = rs + kSampleRows * kDim;          // [32][kQsStride] prepared queries
   float* part = qs + kNQ * kQsStride;           // [32 warps][32 queries] partial dot products
-  __shared__ uint32_t smax[kNQ], s_code[kNQ], s_mask[kNQ], s_rcode[kSampleRows];
+  __shared__ uint32_t smax[kSampleRows / kSampleGroupRows][kNQ], s_code[kNQ], s_mask[kNQ], s_rcode[kSampleRows];
+  __shared__ bool s_last;
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool first = blockIdx.x == 0;
 
-  // 1. sampled rows: a stride over the whole store (or the first rows of a small one)
-  const uint32_t total = kSampleBlocks * kSampleRows;
+  // 1. sampled rows: a stride over the whole store (or the first rows of a small one); 16-byte loads, all issued
+  //    before anything depends on them (one DRAM latency per block, overlapped with the normalisation)
+  const uint32_t total = kSampleGrid * kSampleRows;
   const uint32_t stride = n >= total ? n / total : 1u;
-  float rv[kPrepRowElems];
+  constexpr int kVecPerRow = kDim * (F32 ? 4 : 2) / 16;                 // 16-byte vectors per row (96 | 48)
+  constexpr int kVecPerThread = kSampleRows * kVecPerRow / (32 * kNQ);  // 6 | 3
+  static_assert(kSampleRows * kVecPerRow % (32 * kNQ) == 0, "row vectors must split evenly over the block");
+  uint4 rv[kVecPerThread];
 #pragma unroll
-  for (int e = 0; e < kPrepRowElems; ++e) {
+  for (int e = 0; e < kVecPerThread; ++e) {
     const uint32_t idx = threadIdx.x + 32 * kNQ * e;
-    const uint32_t j = idx / kDim, c = idx - j * kDim;
+    const uint32_t j = idx / kVecPerRow, c = idx - j * kVecPerRow;
     const uint32_t r = (blockIdx.x * kSampleRows + j) * stride;
-    float v = 0.f;
-    if (r < n) {
-      if constexpr (F32) v = __ldg(reinterpret_cast<const float*>(rows) + (size_t)r * kDim + c);
-      else v = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rows) + (size_t)r * kDim + c) << 16);
-    }
-    rv[e] = v;
+    rv[e] = r < n ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(rows) + (size_t)r * (kVecPerRow * 16)) + c)
+                  : make_uint4(0u, 0u, 0u, 0u);
   }
   if (threadIdx.x < kSampleRows) {
     const uint32_t r = (blockIdx.x * kSampleRows + threadIdx.x) * stride;
@@ -1106,19 +1092,35 @@ __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
     const uint32_t c = slot < nq ? code[slot] : 0u, m = slot < nq ? mask[slot] : 0u;
     s_code[slot] = c;
     s_mask[slot] = m;
-    smax[slot] = f32_ordered(-INFINITY);
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) smax[g][slot] = f32_ordered(-INFINITY);
     if (first) {
       qcode[slot] = c;
       qmask[slot] = m;
     }
   }
 #pragma unroll
-  for (int e = 0; e < kPrepRowElems; ++e) rs[threadIdx.x + 32 * kNQ * e] = rv[e];
+  for (int e = 0; e < kVecPerThread; ++e) {
+    const uint32_t idx = threadIdx.x + 32 * kNQ * e;
+    if constexpr (F32) {
+      reinterpret_cast<uint4*>(rs)[idx] = rv[e];
+    } else {  // 8 bf16 -> 8 fp32
+      float4 lo, hi;
+      lo.x = __uint_as_float(rv[e].x << 16); lo.y = __uint_as_float(rv[e].x & 0xFFFF0000u);
+      lo.z = __uint_as_float(rv[e].y << 16); lo.w = __uint_as_float(rv[e].y & 0xFFFF0000u);
+      hi.x = __uint_as_float(rv[e].z << 16); hi.y = __uint_as_float(rv[e].z & 0xFFFF0000u);
+      hi.z = __uint_as_float(rv[e].w << 16); hi.w = __uint_as_float(rv[e].w & 0xFFFF0000u);
+      reinterpret_cast<float4*>(rs)[2 * idx] = lo;
+      reinterpret_cast<float4*>(rs)[2 * idx + 1] = hi;
+    }
+  }
   __syncthreads();
 
-  // 3. score: warp -> (row, half of the 384 elements), lane -> query
-  {
-    const int j = slot >> 1, h = slot & 1;
+  // 3. score: (row, half of the 384 elements) pairs over the 32 warps, lane -> query
+#pragma unroll 1
+  for (int p0 = 0; p0 < kSampleRows * 2; p0 += 32) {
+    const int pr = p0 + slot;
+    const int j = pr >> 1, h = pr & 1;
     const float4* r4 = reinterpret_cast<const float4*>(rs + j * kDim) + h * (kDim / 8);
     const float* qv = qs + lane * kQsStride + h * (kDim / 2);
     float acc = 0.f;
@@ -1131,17 +1133,54 @@ __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
       acc = fmaf(a.w, qv[4 * i + 3], acc);
     }
     part[slot * 32 + lane] = acc;
+    __syncthreads();
+    if (threadIdx.x < 16 * 32) {
+      const int jj = (p0 >> 1) + (threadIdx.x >> 5);  // row; lane = query
+      const int w0 = 2 * (threadIdx.x >> 5);
+      const float sc = part[w0 * 32 + lane] + part[(w0 + 1) * 32 + lane];
+      const uint32_t rc = s_rcode[jj];
+      if (lane < nq && rc != 0xFFFFFFFFu && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u)
+        atomicMax(&smax[jj / kSampleGroupRows][lane], f32_ordered(sc));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < kGroups * kNQ)
+    gsample[(blockIdx.x * kGroups + (threadIdx.x >> 5)) * kNQ + lane] = f32_from_ordered(smax[threadIdx.x >> 5][lane]);
+
+  // 4. the last block turns the block maxima into starting thresholds
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* counter = reinterpret_cast<unsigned int*>(gsample + kSampleCounter);
+    const bool last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (last) {
+      *counter = 0u;  // next launch (stream-ordered per workspace)
+      __threadfence();
+    }
+    s_last = last;
   }
   __syncthreads();
-  if (threadIdx.x < kSampleRows * 32) {
-    const int j = threadIdx.x >> 5;  // row; lane = query
-    const float sc = part[(2 * j) * 32 + lane] + part[(2 * j + 1) * 32 + lane];
-    const uint32_t rc = s_rcode[j];
-    if (lane < nq && rc != 0xFFFFFFFFu && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u)
-      atomicMax(&smax[lane], f32_ordered(sc));
+  if (!s_last) return;
+  {
+    // warp `slot` = query `slot`; lane holds block maxima lane and lane + 32; rank by (value desc, block asc)
+    const float v0 = __ldcg(gsample + lane * kNQ + slot), v1 = __ldcg(gsample + (lane + 32) * kNQ + slot);
+    uint32_t r0 = 0, r1 = 0;
+#pragma unroll 4
+    for (int b = 0; b < 32; ++b) {
+      const float a0 = __shfl_sync(0xffffffffu, v0, b), a1 = __shfl_sync(0xffffffffu, v1, b);
+      r0 += (a0 > v0) || (a0 == v0 && b < lane);
+      r0 += (a1 > v0);
+      r1 += (a0 >= v1);
+      r1 += (a1 > v1) || (a1 == v1 && b < lane);
+    }
+    float kth = -INFINITY;
+    if (r0 == (uint32_t)(k - 1)) kth = v0;
+    if (r1 == (uint32_t)(k - 1)) kth = v1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+    if (lane == 0)
+      gsample[kSampleTau0 + slot] = (slot < nq && kth > -INFINITY) ? __fsub_rd(__fsub_rd(kth, kEpsSample), 3.0f * eps) : -INFINITY;
   }
-  __syncthreads();
-  if (threadIdx.x < kNQ) gsample[blockIdx.x * kNQ + threadIdx.x] = f32_from_ordered(smax[threadIdx.x]);
 }
 
 // one warp per row
@@ -1233,7 +1272,7 @@ cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_sha
 cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, const uint32_t* mask,
                                 int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
                                 unsigned long long* stats, float* gmax, float* gsample, const void* rows,
-                                const uint32_t* codes, uint32_t n, cudaStream_t st) {
+                                const uint32_t* codes, uint32_t n, int k, float eps, cudaStream_t st) {
   const size_t smem = kPrepSmem;
   static bool configured[64] = {};
   int dev = 0;
@@ -1247,11 +1286,11 @@ cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, 
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (f32)
-    prep_queries_kernel<true><<<kSampleBlocks, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
-                                                                     gmax, gsample, rows, codes, n);
+    prep_queries_kernel<true><<<kSampleGrid, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
+                                                                     gmax, gsample, rows, codes, n, k, eps);
   else
-    prep_queries_kernel<false><<<kSampleBlocks, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
-                                                                      gmax, gsample, rows, codes, n);
+    prep_queries_kernel<false><<<kSampleGrid, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
+                                                                      gmax, gsample, rows, codes, n, k, eps);
   return cudaGetLastError();
 }
 

@@ -25,8 +25,15 @@ constexpr int kGmaxPad = 32 * kGmaxPerLane;     // floats per query
 constexpr int kMaxTileSlots = 944;              // tiles per CTA of a restricted scan (what shared memory leaves)
 
 // bootstrap sample scored by the prep kernel: kSampleBlocks blocks x kSampleRows rows
-constexpr int kSampleBlocks = 64;
-constexpr int kSampleRows = 16;   // per block: 4 warps x 4 rows
+constexpr int kSampleBlocks = 64;  // groups of sampled rows; each publishes its best matching score per query
+constexpr int kSampleGrid = 16;    // CTAs of the prep kernel: few and fat, so that it is short even when it is
+                                   // squeezed onto the handful of SMs a running scan leaves free
+constexpr int kSampleRows = 64;    // rows per CTA = 4 groups of 16 (1024 rows in all)
+constexpr int kSampleGroupRows = kSampleRows * kSampleGrid / kSampleBlocks;
+// gsample buffer: [kSampleBlocks][32] block maxima | tau0 [32] starting thresholds | block counter (u32)
+constexpr int kSampleTau0 = kSampleBlocks * kNQ;
+constexpr int kSampleCounter = kSampleTau0 + kNQ;
+constexpr int kSampleFloats = kSampleCounter + 1;
 constexpr float kEpsSample = 3.0e-5f;  // |fp32 FMA-chain score - fp64 score| bound (384 terms)
 
 // bound on |tensor-core pre-filter score - fp64 score| for unit-norm rows and queries
@@ -50,7 +57,7 @@ struct ScanParams {
   uint64_t* part_keys;     // [grid, 32, kListCap] surviving (approx score, row) keys per CTA, unsorted
   uint32_t* part_cnt;      // [grid, 32]
   float* gmax;             // [kGmaxPad, 32] best appended pre-filter score per (CTA, query)
-  const float* gsample;    // [kSampleBlocks, 32] best fp32 score per (sample block, query), or -inf
+  const float* tau0;       // [32] starting pass thresholds from the prep kernel's bootstrap sample (-inf = none)
   float* dbg_scores;       // DUMP mode only: [32, n]
   unsigned long long* stats;  // [kStatSlots]
   unsigned long long* timeline;  // diagnostics: [grid, 8] globaltimer stamps, or null
@@ -121,7 +128,7 @@ cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_sha
 cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, const uint32_t* mask,
                                 int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
                                 unsigned long long* stats, float* gmax, float* gsample, const void* rows,
-                                const uint32_t* codes, uint32_t n, cudaStream_t st);
+                                const uint32_t* codes, uint32_t n, int k, float eps, cudaStream_t st);
 // rows [n,384] fp32 -> L2-normalised storage rows (+ codes) at dst row offset
 cudaError_t launch_store_rows(bool f32, const float* vecs, const uint32_t* codes, int64_t n,
                               void* rows_dst, uint32_t* codes_dst, cudaStream_t st);

@@ -148,6 +148,9 @@ class VectorIndex:
         """SMs the persistent scan kernel leaves to the prep / merge / exchange kernels in the pipelined forms."""
         check(self._lib.frs_index_set_pipeline_reserve(self._h, int(sms)))
 
+    def set_scan_streams(self, n: int) -> None:
+        check(self._lib.frs_index_set_scan_streams(self._h, int(n)))
+
     # -- search ---------------------------------------------------------------------------------
     @staticmethod
     def _check_batch(nq: int, k: int) -> None:

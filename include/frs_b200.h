@@ -91,9 +91,13 @@ int frs_index_set_base(frs_index* idx, int64_t base);
 /* number of CTAs of the scan kernel (0 = one per SM).  Results do not depend on it; exposed so
  * the tests can prove that. */
 int frs_index_set_scan_grid(frs_index* idx, int grid);
-/* SMs the persistent scan kernel leaves free in the PIPELINED entry points (default 4), so that the neighbouring
- * batches' prepare / merge / exchange kernels can run beside it.  Results do not depend on it. */
+/* SMs the persistent scan kernel leaves free in the PIPELINED entry points, so that the neighbouring batches'
+ * prepare / merge / exchange kernels can run beside it; -1 (default) = chosen from the shard size (4 for long
+ * scans, up to 12 for short ones).  Results do not depend on it. */
 int frs_index_set_pipeline_reserve(frs_index* idx, int sms);
+/* 2 (default): consecutive pipelined scans alternate between two streams, so the first CTAs of scan i+1 start on
+ * the SMs the last CTAs of scan i leave; 1: strictly one scan after the other (measurement knob). */
+int frs_index_set_scan_streams(frs_index* idx, int n);
 
 /* qdrant.upsert(points)  ingest.py:171-175: L2-normalise (cosine collection),
  * convert to the storage dtype and append.  vecs: [n, 384] fp32, codes: [n]. */
