@@ -102,7 +102,7 @@ class ClockSampler:
     def _loop(self):
         while not self.stop.is_set():
             self.sample()
-            self.stop.wait(0.002 if self.nv is not None else 0.1)
+            self.stop.wait(0.01 if self.nv is not None else 0.1)
 
     def start(self):
         self.thread.start()
@@ -401,8 +401,10 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     cx.barrier()
     cx.aligned_start()
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(steps):
         last = step()
+    host_us = (time.perf_counter() - h0) / steps * 1e6   # host time to enqueue one step (must stay under the GPU's)
     drain()
     e1.record()
     if cx.rank == 0:
@@ -427,7 +429,7 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     stats = ix.last_stats()
     launches = stats["launches"]
 
-    out = {"ms": ms, "ids": ids, "scores": scores, "samples": samples, "launches_per_step": launches, "stats": stats,
+    out = {"host_enqueue_us_per_step": cx.max_over_ranks(host_us), "ms": ms, "ids": ids, "scores": scores, "samples": samples, "launches_per_step": launches, "stats": stats,
            "breakdown": {"prep": prof["prep_ms"] / n, "scan": prof["scan_ms"] / n, "merge": prof["merge_ms"] / n,
                          "exchange": prof["exchange_ms"] / n, "gap": prof["scan_gap_ms"] / max(n - 1, 1),
                          "step": prof["span_ms"] / n}}
@@ -619,6 +621,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": r["alg_bytes"], "peak_source": peak_src,
                          "whole_step_frac": r["alg_bytes"] / (ms / steps * 1e-3) / 1e9 / peak},
             "breakdown_ms": {k: round(v, 5) for k, v in r["breakdown"].items()},
+            "host_enqueue_us_per_step": round(r["host_enqueue_us_per_step"], 1),
             "scan_stats_last_step": {k: r["stats"][k] for k in ("appended", "compactions", "resolutions", "rescored", "grid")},
             "parity_checked": checked, "prefilter_max_err": pre_err, "prefilter_eps": 3e-5,
             "comm": ("peer-memory stores + flags inside the merge kernel (csrc/exchange.cu); NCCL is used for process-group set-up and "

@@ -9,7 +9,7 @@
 //   gemm_kernel<ResLN>     BertSelfOutput / BertOutput       :294-298, :352-356  (bias+residual+LayerNorm)
 //   gemm_kernel<Gelu>      BertIntermediate (erf GELU)       :339-342
 //   pool_normalize_kernel  sentence-transformers Pooling(cls|mean) + Normalize
-//   ce_head_kernel         BertPooler + classifier           :462-468, :1111-1124
+//   (BertPooler + classifier :462-468, :1111-1124 run in fp32 from the fp32 [CLS] rows: bert_fp32.cu ce_head_f32_kernel)
 //
 // Every GEMM is tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM) fed by TMA into
 // SWIZZLE_128B shared-memory slabs; warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM
@@ -170,13 +170,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 __global__ void row_map_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ row_start, int n_seqs,
                                int32_t* __restrict__ src_tok, int32_t* __restrict__ pos_of_row,
-                               int32_t* __restrict__ row_of_tok) {
+                               int32_t* __restrict__ row_of_tok, int32_t* __restrict__ cls_slot) {
   const int s = blockIdx.x;
   if (s >= n_seqs) return;
   const int t0 = cu[s], len = cu[s + 1] - cu[s], r0 = row_start[s], slot = row_start[s + 1] - r0;
   for (int i = threadIdx.x; i < slot; i += blockDim.x) {
     src_tok[r0 + i] = i < len ? t0 + i : -1;
     pos_of_row[r0 + i] = i;
+    cls_slot[r0 + i] = i == 0 ? s : -1;  // the [CLS] row of sequence s (see the ResLN epilogue)
     if (i < len) row_of_tok[t0 + i] = r0 + i;
   }
 }
@@ -264,7 +265,7 @@ struct GemmCfg {
   static constexpr int kOutBytes = kBM * kNSub * 2;    // 48 KB: 2 groups x 3 boxes of 128 rows x 32 bf16
   static constexpr int kParF = kOut + kOutBytes;       // fp32 params: bias[1536] | gamma[384] | beta[384]
   static constexpr int kStat = kParF + (1536 + 768) * 4;  // LN: per-row partial statistics of the two column halves
-  static constexpr int kBars = kStat + (LN ? 2 * 2 * 128 * 8 : 0);  // [2 tile parities][2 halves][128 rows] float2
+  static constexpr int kBars = kStat + (LN ? 2 * 2 * 128 * 16 : 0);  // [2 tile parities][2 halves][128 rows] float4 (sum, sumsq, shift, -)
   static constexpr int kHolder = kBars + (2 * kStages + 2 * kAcc) * 8;
   static constexpr int kTotal = kHolder + 16;
   static_assert(kTotal + 1024 <= 232448, "shared memory budget");
@@ -313,7 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   float* sbias = reinterpret_cast<float*>(sm + C::kParF);
   float* sgamma = sbias + 1536;
   float* sbeta = sgamma + 384;
-  float2* sstat = reinterpret_cast<float2*>(sm + C::kStat);
+  float4* sstat = reinterpret_cast<float4*>(sm + C::kStat);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + C::kBars);
   uint64_t* empty = full + C::kStages;
   uint64_t* tfull = empty + C::kStages;
@@ -680,18 +681,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // column-half group (same lane quarter) the other 192.  Pass 1: bias (the residual is already in the
         // accumulator) and row statistics; pass 2 reads the accumulator again and repeats the one bias FADD2 per
         // pair (bit-identical), which is cheaper than writing the pre-LayerNorm value back to TMEM in between.
+        // Statistics are SHIFTED: the thread accumulates sum(x - c) and sum((x - c)^2) with c = the mean of its own
+        // first 32 values, so a row whose values share a large offset (|mean| >> spread) loses nothing to the
+        // cancellation of E[x^2] - mean^2, and a single outlier dimension moves c by 1/32 of itself at most.  The
+        // two halves' (sum, sumsq, c) are combined exactly: mean = (c0 + c1)/2 + (S0 + S1)/384,
+        // sum (x - mean)^2 over half h = Q_h - 2 d_h S_h + 192 d_h^2 with d_h = mean - c_h.
         float sum = 0.f, sq = 0.f, sum1 = 0.f, sq1 = 0.f;  // even / odd columns (packed pairs)
+        float shift = 0.f;
+        // the CLS row of a sequence keeps an fp32 copy of the LAST layer's output (pooler / classifier / pooling read
+        // it instead of the bf16-rounded row: that rounding was the largest single term of the logit error)
+        int cls_slot = -1;
+        if (p.cls_slot) {
+          const int grow = tile_mt(tile) * kBM + (int)row;
+          if (grow < p.M) cls_slot = __ldg(p.cls_slot + grow);
+        }
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
           const int col = (int)half * C::kColsPerThread + c * 32;  // column of the 384-wide row
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           const float* bs = sbias + col;
+          if (c == 0) {
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+              const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
+              fadd2(a, b, bb.x, bb.y);
+              fadd2(p0, p1, a, b);
+            }
+            shift = (p0 + p1) * (1.0f / 32.0f);
+          }
+          const float nshift = -shift;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
             const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
             fadd2(a, b, bb.x, bb.y);
+            fadd2(a, b, nshift, nshift);
             fadd2(sum, sum1, a, b);
             ffma2_acc(sq, sq1, a, b, a, b);
           }
@@ -701,15 +728,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         sq += sq1;
         // the two column halves of a row meet in shared memory (double-buffered by tile parity: a fast group may
         // be one tile ahead of the other group's read)
-        float2* st = sstat + (lt & 1) * 256;
-        st[half * 128 + row] = make_float2(sum, sq);
+        float4* st = sstat + (lt & 1) * 256;
+        st[half * 128 + row] = make_float4(sum, sq, shift, 0.f);
         named_bar_sync(1, kGemmEpiThreads);
         FRS_GT(18);
-        const float2 s0 = st[row], s1 = st[128 + row];
-        const float tsum = s0.x + s1.x;  // the same two operands in the same order in both groups
-        const float tsq = s0.y + s1.y;
-        const float mean = tsum * (1.0f / kHid);
-        const float var = fmaxf(tsq * (1.0f / kHid) - mean * mean, 0.f);
+        const float4 s0 = st[row], s1 = st[128 + row];
+        // the same operands in the same order in both groups: bit-identical mean / rstd for the two halves of a row
+        const float mean = 0.5f * (s0.z + s1.z) + (s0.x + s1.x) * (1.0f / kHid);
+        const float d0 = mean - s0.z, d1 = mean - s1.z;
+        const float ss0 = fmaf(d0, fmaf(d0, (float)(kHid / 2), -2.0f * s0.x), s0.y);
+        const float ss1 = fmaf(d1, fmaf(d1, (float)(kHid / 2), -2.0f * s1.x), s1.y);
+        const float var = fmaxf((ss0 + ss1) * (1.0f / kHid), 0.f);
         const float rstd = rsqrtf(var + p.eps);
 #pragma unroll 1
         for (int c = 0; c < C::kColsPerThread / 32; ++c) {
@@ -733,6 +762,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             fadd2(a, b, -mean, -mean);
             fmul2(a, b, rstd, rstd);
             ffma2(a, b, gg.x, gg.y, be.x, be.y);
+            if (cls_slot >= 0) *reinterpret_cast<float2*>(p.cls_out + (size_t)cls_slot * kHid + col + 2 * j) = make_float2(a, b);
             o[j] = pack_bf16x2(a, b);
           }
           stage_and_store(o);
@@ -1225,37 +1255,6 @@ pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __rest
   for (int i = 0; i < 3; ++i) out[(size_t)s * kHid + threadIdx.x + 128 * i] = v[i] * inv;
 }
 
-__global__ void __launch_bounds__(384)
-ce_head_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ row_start, int n_seqs,
-               const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ wc,
-               const float* __restrict__ bc, float* __restrict__ logits) {
-  __shared__ float xs[kHid];
-  __shared__ float pooled[kHid];
-  __shared__ float red[12];
-  const int s = blockIdx.x;
-  if (s >= n_seqs) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  xs[threadIdx.x] = __bfloat162float(x[(size_t)row_start[s] * kHid + threadIdx.x]);
-  __syncthreads();
-  for (int o = warp * 32; o < warp * 32 + 32; ++o) {
-    const float* w = wp + (size_t)o * kHid;
-    float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) a = fmaf(__ldg(w + lane + 32 * i), xs[lane + 32 * i], a);
-    a = warp_sum(a);
-    if (lane == 0) pooled[o] = tanhf(a + bp[o]);
-  }
-  __syncthreads();
-  float a = warp_sum(pooled[threadIdx.x] * wc[threadIdx.x]);
-  if (lane == 0) red[warp] = a;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 12; ++i) t += red[i];
-    logits[s] = t + bc[0];
-  }
-}
-
 __global__ void gather_rows_f32_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ row_of_tok,
                                        int n_tokens, float* __restrict__ out) {
   const int t = blockIdx.x;
@@ -1282,9 +1281,9 @@ size_t gemm_smem_bytes(int epi) {
 size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
 
 cudaError_t launch_row_map(const int32_t* cu_seqlens, const int32_t* row_start, int n_seqs, int32_t* src_tok,
-                           int32_t* pos_of_row, int32_t* row_of_tok, cudaStream_t st) {
+                           int32_t* pos_of_row, int32_t* row_of_tok, int32_t* cls_slot, cudaStream_t st) {
   if (n_seqs <= 0) return cudaSuccess;
-  row_map_kernel<<<n_seqs, 128, 0, st>>>(cu_seqlens, row_start, n_seqs, src_tok, pos_of_row, row_of_tok);
+  row_map_kernel<<<n_seqs, 128, 0, st>>>(cu_seqlens, row_start, n_seqs, src_tok, pos_of_row, row_of_tok, cls_slot);
   return cudaGetLastError();
 }
 
@@ -1431,14 +1430,6 @@ cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seql
                                   int n_seqs, int pool_mode, float* out, cudaStream_t st) {
   if (n_seqs <= 0) return cudaSuccess;
   pool_normalize_kernel<<<n_seqs, 128, 0, st>>>(x, cu_seqlens, row_start, n_seqs, pool_mode, out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* row_start, int n_seqs, const float* wp,
-                           const float* bp, const float* wc, const float* bc, float* logits,
-                           cudaStream_t st) {
-  if (n_seqs <= 0) return cudaSuccess;
-  ce_head_kernel<<<n_seqs, 384, 0, st>>>(x, row_start, n_seqs, wp, bp, wc, bc, logits);
   return cudaGetLastError();
 }
 

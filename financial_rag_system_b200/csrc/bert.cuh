@@ -40,6 +40,8 @@ struct GemmParams {
   const float* gamma;
   const float* beta;
   float eps;
+  const int32_t* cls_slot;  // ResLN, last layer only: [rows] sequence index of a [CLS] row, else -1 (null = off)
+  float* cls_out;           //   fp32 copies of the [CLS] rows' outputs, [n_seqs, 384]
   int debug;  // FRS_GEMM_DEBUG (measurement aid): 1 = epilogue only drains TMEM (no math, no stores)
   long long* trace;  // -DFRS_GEMM_TRACE builds: event timeline of CTA 0 (see launch_gemm_t), else null
 };
@@ -68,9 +70,10 @@ size_t attn_smem_bytes();
 // sequence's arithmetic does not depend on where it sits in the batch).  cu_seqlens is the caller's
 // packed layout.  One block per sequence fills, for every internal row of the sequence's slot,
 // src_tok[row] (caller token index, -1 for the <= 7 alignment rows), pos_of_row[row] (position in the
-// sequence) and, for every caller token, row_of_tok[token].
+// sequence), cls_slot[row] (the sequence index on its first row, -1 elsewhere) and, for every caller token,
+// row_of_tok[token].
 cudaError_t launch_row_map(const int32_t* cu_seqlens, const int32_t* row_start, int n_seqs, int32_t* src_tok,
-                           int32_t* pos_of_row, int32_t* row_of_tok, cudaStream_t st);
+                           int32_t* pos_of_row, int32_t* row_of_tok, int32_t* cls_slot, cudaStream_t st);
 // x[row] = LayerNorm(word[id] + pos[p] + type[tt]) -> bf16 for the M internal rows (alignment rows = 0);
 // type_ids may be null (all 0)
 cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const int32_t* src_tok,
@@ -92,9 +95,7 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
 cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, const int32_t* row_start,
                                   int n_seqs, int pool_mode, float* out, cudaStream_t st);
 // logits[s] = wc . tanh(Wp * x[cls_s] + bp) + bc
-cudaError_t launch_ce_head(const __nv_bfloat16* x, const int32_t* row_start, int n_seqs, const float* wp,
-                           const float* bp, const float* wc, const float* bc, float* logits,
-                           cudaStream_t st);
+
 // out[t] = fp32(x[row_of_tok[t]]) for the caller's packed tokens
 cudaError_t launch_gather_rows_f32(const __nv_bfloat16* x, const int32_t* row_of_tok, int n_tokens, float* out,
                                    cudaStream_t st);

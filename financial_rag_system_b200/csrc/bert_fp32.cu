@@ -237,7 +237,8 @@ pool_normalize_f32_kernel(const float* __restrict__ x, const int32_t* __restrict
   __shared__ float red[4];
   const int s = blockIdx.x;
   if (s >= n_seqs) return;
-  const int t0 = row_start[s], t1 = t0 + (cu[s + 1] - cu[s]);
+  // row_start == null: x holds one row per sequence (the fp32 [CLS] rows of the bf16 path)
+  const int t0 = row_start ? row_start[s] : s, t1 = t0 + (cu[s + 1] - cu[s]);
   float v[3] = {0.f, 0.f, 0.f};
   if (pool_mode == 0) {
 #pragma unroll
@@ -268,7 +269,7 @@ ce_head_f32_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_
   const int s = blockIdx.x;
   if (s >= n_seqs) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  xs[threadIdx.x] = x[(size_t)row_start[s] * kHid + threadIdx.x];
+  xs[threadIdx.x] = x[(size_t)(row_start ? row_start[s] : s) * kHid + threadIdx.x];
   __syncthreads();
   for (int o = warp * 32; o < warp * 32 + 32; ++o) {
     float a = 0.f;

@@ -58,7 +58,8 @@ struct frs_encoder {
   __nv_bfloat16 *x0 = nullptr, *x1 = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *h = nullptr;
   float *fx0 = nullptr, *fx1 = nullptr, *fqkv = nullptr, *fctx = nullptr, *fh = nullptr, *ftmp = nullptr;  // fp32 mode
   bool f32() const { return cfg.precision == FRS_PRECISION_F32; }
-  int32_t *pos_of_row = nullptr, *src_tok = nullptr, *row_of_tok = nullptr;
+  int32_t *pos_of_row = nullptr, *src_tok = nullptr, *row_of_tok = nullptr, *cls_slot = nullptr;
+  float* cls_f32 = nullptr;  // [max_seqs, 384] fp32 copies of the last layer's [CLS] rows (bf16 path)
   int32_t *d_cu = nullptr, *d_rs = nullptr;  // caller cu_seqlens | internal row starts (multiples of 8)
   QBlock* d_qblk = nullptr;
   CUtensorMap t_x0, t_x1, t_ctx, t_h, t_qk, t_vt;  // box 64 x 128 (vt: 64 x 64): GEMM A operands, attention loads
@@ -257,6 +258,8 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   EN_TRY(dev_alloc(e, &e->pos_of_row, T * 4, true));
   EN_TRY(dev_alloc(e, &e->src_tok, T * 4, true));
   EN_TRY(dev_alloc(e, &e->row_of_tok, T * 4, true));
+  EN_TRY(dev_alloc(e, &e->cls_slot, T * 4, true));
+  EN_TRY(dev_alloc(e, &e->cls_f32, (size_t)e->max_seqs * kHid * 4, true));
   EN_TRY(dev_alloc(e, &e->d_cu, ((size_t)e->max_seqs + 1) * 4, true));
   EN_TRY(dev_alloc(e, &e->d_rs, ((size_t)e->max_seqs + 1) * 4, true));
   EN_TRY(dev_alloc(e, &e->d_qblk, (size_t)e->max_qblk * sizeof(QBlock), true));
@@ -365,7 +368,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
   if (getenv("FRS_DEBUG_SYNC")) bert_trap_info_host();  // arm the wait-timeout recorder
   if (e->prof) CU_TRY(cudaEventRecord(e->pev[0], st));
   int rc;
-  CU_TRY(launch_row_map(e->d_cu, e->d_rs, n_seqs, e->src_tok, e->pos_of_row, e->row_of_tok, st));
+  CU_TRY(launch_row_map(e->d_cu, e->d_rs, n_seqs, e->src_tok, e->pos_of_row, e->row_of_tok, e->cls_slot, st));
   if (e->f32()) {
     // fp32 mode: the same graph with fp32 FFMA kernels (bert_fp32.cu); LayerNorm is a separate kernel here
     CU_TRY(launch_embed_ln_f32(d_ids, d_type, e->src_tok, e->pos_of_row, M, e->cfg.vocab_size, e->word, e->pos, e->type,
@@ -433,6 +436,10 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     g.resid = e->x1;
     g.gamma = L.ln2g;
     g.beta = L.ln2b;
+    if (l == e->cfg.layers - 1) {  // the last layer's [CLS] rows also leave in fp32 (head / CLS pooling operand)
+      g.cls_slot = e->cls_slot;
+      g.cls_out = e->cls_f32;
+    }
     CU_TRY(launch_gemm(kEpiResLN, e->sm_count, e->t_h, L.t_w2, e->s_x0, e->t_x1, g, st));
     if ((rc = prof_mark(e, kPDown, st))) return rc;
   }
@@ -451,6 +458,8 @@ extern "C" int frs_encoder_embed(frs_encoder* enc, const int32_t* dev_ids, const
   if (rc) return rc;
   if (enc->f32())
     CU_TRY(launch_pool_normalize_f32(enc->fx0, enc->d_cu, enc->d_rs, n_seqs, pool_mode, dev_out, st));
+  else if (pool_mode == FRS_POOL_CLS)  // fp32 [CLS] rows kept by the last LayerNorm epilogue, dense [n_seqs, 384]
+    CU_TRY(launch_pool_normalize_f32(enc->cls_f32, enc->d_cu, nullptr, n_seqs, pool_mode, dev_out, st));
   else
     CU_TRY(launch_pool_normalize(enc->x0, enc->d_cu, enc->d_rs, n_seqs, pool_mode, dev_out, st));
   if ((rc = prof_mark(enc, kPHead, st))) return rc;
@@ -470,8 +479,8 @@ extern "C" int frs_encoder_score_pairs(frs_encoder* enc, const int32_t* dev_ids,
   if (rc) return rc;
   if (enc->f32())
     CU_TRY(launch_ce_head_f32(enc->fx0, enc->d_rs, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
-  else
-    CU_TRY(launch_ce_head(enc->x0, enc->d_rs, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
+  else  // pooler + classifier in fp32 from the fp32 [CLS] rows (dense [n_seqs, 384]: no row table)
+    CU_TRY(launch_ce_head_f32(enc->cls_f32, nullptr, n_seqs, enc->pool_w, enc->pool_b, enc->cls_w, enc->cls_b, dev_logits, st));
   if ((rc = prof_mark(enc, kPHead, st))) return rc;
   CU_TRY(cudaEventRecord(enc->ws_free, st));
   return FRS_OK;

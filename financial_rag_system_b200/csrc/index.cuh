@@ -45,7 +45,7 @@ struct HostSlot {
 };
 constexpr size_t kHostInBytes = (size_t)kNQ * kDim * 4 + 2 * kNQ * 4;
 constexpr size_t kHostOutBytes = (size_t)kNQ * kMaxK * (8 + 4);
-constexpr int kWsRing = 3;      // searches in flight per index (prep | scan | merge)
+constexpr int kWsRing = 4;      // searches in flight per index (prep | scan | scan | merge)
 constexpr int kHostSlots = 4;   // host calls in flight per index
 constexpr int kJobRing = 16;    // event sets of the pipelined form
 constexpr int kProfEvents = 8;  // per recorded search: pre/post prep, pre/post scan, pre/post merge, post exchange

@@ -329,3 +329,34 @@ def test_bf16_path_deviates_from_the_fp32_path_by_rounding_only(bge):
     a, b = enc.embed_packed(ids, cu), e32.embed_packed(ids, cu)
     e32.close()
     assert np.abs(a - b).max() <= 1e-2 and ((a * b).sum(1)).min() >= 0.999
+
+
+@pytest.mark.parametrize("kind", ["outlier_dim", "large_offset"])
+def test_layernorm_epilogue_survives_outlier_dimensions_and_large_offsets(kind):
+    """Real BERT checkpoints have outlier hidden dimensions (one LayerNorm gain tens of times the others) and rows
+    whose mean is far from zero.  The fused ResLN epilogue keeps SHIFTED single-pass statistics; this checks it on
+    weights built to break E[x^2] - mean^2: a 50x gain on one dimension of every LayerNorm, or a +30 bias on all."""
+    from financial_rag_system_b200.checkpoint import BertShape, synthetic_checkpoint
+    from financial_rag_system_b200.encoder import BertEncoder
+    from oracle import encoder_oracle as eo
+
+    shape = BertShape(layers=3, has_head=False)
+    w = synthetic_checkpoint(shape, 77)
+    for name in list(w):
+        if name.endswith("LayerNorm.weight") and kind == "outlier_dim":
+            w[name] = w[name].copy()
+            w[name][17] *= 50.0
+        if name.endswith("LayerNorm.bias") and kind == "large_offset":
+            w[name] = (w[name] + 30.0).astype(np.float32)
+    ids, _, cu = _random_batch([64, 300, 9, 128], 5)
+    enc = BertEncoder(shape, w, device=0, max_tokens=1024)
+    got = enc.embed_packed(ids, cu, 0)
+    hid = enc.last_hidden(int(cu[-1])).cpu().numpy()
+    enc.close()
+    ref = eo.embed(shape, w, ids, cu, "cls")
+    ref_h = eo.last_hidden_packed(shape, w, ids, cu)
+    rel = np.abs(hid - ref_h).max() / np.abs(ref_h).max()
+    print(f"{kind}: |hidden| up to {np.abs(ref_h).max():.1f}, max rel err {rel:.4f}, embedding max err {np.abs(got - ref).max():.2e}, "
+          f"min cos {(got * ref).sum(1).min():.6f}")
+    assert (got * ref).sum(1).min() >= 0.999
+    assert rel <= 0.02

@@ -100,3 +100,25 @@ def test_identical_text_is_its_own_nearest_neighbour(stack):
     for k, i in enumerate(sel):
         assert abs(sc[k, 0] - 1.0) < 2e-3
         assert i in got[k][np.abs(sc[k] - sc[k, 0]) < 1e-6]
+
+
+def test_evaluation_harness_scores_self_queries_perfectly():
+    """evaluate.py:59-128 on the drop-in surface with the GPU embedder for corpus AND queries: a chunk asked for with
+    its own text must come back first (Hit@5 = 100 %, MRR = 1.0), whatever the weights."""
+    from financial_rag_system_b200 import synth
+    from financial_rag_system_b200.collection import QdrantCompat, models
+    from financial_rag_system_b200.encoder import Embedder
+    from financial_rag_system_b200.evaluate import COLLECTION_NAME, run_evaluation, synthetic_eval_set
+
+    n = 600
+    ids, texts, payloads = synth.make_chunks(n, n_tickers=8, seed=5)
+    emb = Embedder(device=0, max_tokens=32768)
+    q = QdrantCompat(capacity=n)
+    q.create_collection(COLLECTION_NAME, models.VectorParams(size=384, distance=models.Distance.COSINE))
+    for s in range(0, n, 256):
+        vecs = emb.encode(texts[s:s + 256])
+        q.upsert(COLLECTION_NAME, [models.PointStruct(id=ids[i], vector=vecs[i - s].tolist(), payload=payloads[i])
+                                   for i in range(s, min(n, s + 256))])
+    r = run_evaluation(q, emb, synthetic_eval_set(texts, payloads, 40), k=5)
+    assert r["hit_rate"] == 100.0 and r["mrr"] == 1.0
+    emb.close()

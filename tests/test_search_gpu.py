@@ -479,3 +479,41 @@ def test_collection_on_gpu_uses_the_restricted_scan():
     assert seg.last_scan_tiles == (total, total)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     seg.close()
+
+
+@pytest.mark.parametrize("dtype,eps", [("bf16", 3.0e-5), ("f32", 2.0e-3)])
+def test_prefilter_bound_holds_for_same_sign_rows_with_scores_near_one(dtype, eps):
+    """The adversarial case for an fp32 accumulator that might truncate: every product has the same sign and the
+    partial sums grow towards 1 (worst relative rounding), on 1M rows.  The exactness argument only needs
+    |tensor-core score - fp64 score| <= eps; the search on the same data (a dense band of near-equal scores:
+    list compactions, exact in-scan resolutions, ties) must equal the fp64 ranking."""
+    n, nq, k = 1_000_000, 32, 15
+    g = torch.Generator(device="cuda").manual_seed(41)
+    base = torch.rand((1, 384), generator=g, device="cuda") + 0.5          # all positive
+    x = base + 0.02 * torch.rand((n, 384), generator=g, device="cuda")     # all positive, cos(row, row') ~ 0.9999
+    x[5000] = x[17]                                                       # exact duplicates: ties
+    x[900_000] = x[17]
+    codes = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    ix = _index(n, dtype)
+    ix.add(x, codes)
+    q = x[:nq] + 0.01 * torch.rand((nq, 384), generator=g, device="cuda")
+    approx = ix.debug_scores(q)[:nq].double()                              # [32, n]
+    qp = ix.last_queries()[:nq].double()
+    exact = torch.empty((nq, n), dtype=torch.float64, device="cuda")
+    for s in range(0, n, 1 << 18):                                         # fp64 products of fp32 values are exact
+        exact[:, s:s + (1 << 18)] = (ix.read_rows(s, min(1 << 18, n - s)).double() @ qp.T).T
+    err = float((approx - exact).abs().max())
+    print(f"same-sign {dtype}: scores in [{float(exact.min()):.5f}, {float(exact.max()):.5f}], max |pre-filter - fp64| = {err:.3e} (eps {eps:.1e})")
+    assert err <= eps / 2, err
+    ids, sc = ix.search(q, _i32(np.zeros(nq)), _i32(np.full(nq, ANY, np.uint32)), k)
+    torch.cuda.synchronize()
+    top_s, top_i = torch.topk(exact, 256, dim=1)                           # candidates; final order on the host
+    top_s, top_i = top_s.cpu().numpy(), top_i.cpu().numpy()
+    for qi in range(nq):
+        order = np.lexsort((top_i[qi], -top_s[qi]))[:k]
+        assert top_s[qi][order][-1] > top_s[qi].min(), "candidate window too small for this band"
+        assert np.array_equal(ids[qi].cpu().numpy(), top_i[qi][order]), qi
+        assert np.allclose(sc[qi].cpu().numpy(), top_s[qi][order], atol=SCORE_ATOL)
+    st = ix.last_stats()
+    print("   scan stats:", st)
+    ix.close()
