@@ -18,7 +18,7 @@ FRS_DTYPE_F32 = 0
 FRS_DTYPE_BF16 = 1
 FRS_DIM = 384
 FRS_MAX_BATCH = 32
-FRS_MAX_K = 16
+FRS_MAX_K = 32
 CODE_TICKER_MASK = 0x00FFFFFF
 CODE_DOCTYPE_SHIFT = 24
 CODE_DOCTYPE_MASK = 0x7F000000

@@ -12,7 +12,7 @@ constexpr int kTileM = 128;     // corpus rows per tile == MMA M
 constexpr int kSlabBytes = kTileM * 128;  // 128 rows x 128 B: one SWIZZLE_128B K-slab (16 KiB)
 constexpr int kListCap = 64;    // per-query candidate list capacity inside a CTA
 constexpr int kKeep = 32;       // most entries a list keeps after a compaction
-constexpr int kMaxK = 16;       // largest `limit` supported              reference main.py:215
+constexpr int kMaxK = 32;       // largest `limit` supported (the reference asks for 15, main.py:215; 5, evaluate.py:86)
 constexpr int kAccStages = 16;  // TMEM accumulator ring (16 x 32 columns = all 512)
 constexpr int kTmemCols = kAccStages * kNQ;
 constexpr int kEpiWarps = 8;      // epilogue warps: 4 TMEM lane groups x 2 query-column groups

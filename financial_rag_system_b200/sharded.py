@@ -56,10 +56,10 @@ class PendingSearch:
 class PeerExchange:
     """The exchange step over NVLink peer memory (include/frs_b200.h frs_exchange_*): push = this rank's
     block into every peer's gather buffer + a sequence flag; wait_merge = wait for all ranks' flags, then the
-    cross-shard merge.  ONE object serves every batch size <= nq and limit <= k (default 32 / 16 = the ABI's
+    cross-shard merge.  ONE object serves every batch size <= nq and limit <= k (default 32 / 32 = the ABI's
     maxima), so nothing is created in the request path.  Every rank pushes / merges once per batch, same order."""
 
-    def __init__(self, device: torch.device, world: int, rank: int, nq: int = 32, k: int = 16, group=None,
+    def __init__(self, device: torch.device, world: int, rank: int, nq: int = 32, k: int = 32, group=None,
                  connect: bool = True, timeout_ms: Optional[int] = None):
         import ctypes as C
 
@@ -151,7 +151,7 @@ class ShardedIndex:
         when local_search/merge are injected).
 
         exchange: "p2p" (default on CUDA) = stores into the peers' buffers over NVLink peer memory, fused into the
-        local merge kernel, flags + a bounded wait (csrc/exchange.cu); ONE exchange object (32 queries x 16) is
+        local merge kernel, flags + a bounded wait (csrc/exchange.cu); ONE exchange object (32 queries x 32) is
         created here, collectively, and serves every batch.  "nccl" = one all-gather of the packed
         (score, id) lists per batch (the form north_star names; also what the injectable CPU path under gloo
         uses).  "auto" = p2p, falling back to nccl on every rank if CUDA IPC is unavailable on any.

@@ -9,7 +9,7 @@ Semantics follow `transformers.BertTokenizer(do_lower_case=True)` (tokenization_
 BertNormalizer (clean text, lower-case, strip accents, split CJK), whitespace + punctuation
 pre-tokenisation, greedy longest-match WordPiece with `##` continuation pieces and `[UNK]` for words
 over 100 characters, `[CLS] a [SEP]` / `[CLS] a [SEP] b [SEP]` with token types 0/1, truncation to 512
-(`longest_first` for pairs).  tests/test_tokenizer_cpu.py checks the ids against BertTokenizer.
+(`longest_first` for pairs).  tests/test_encoder_oracle_cpu.py checks the ids against BertTokenizer.
 
 This image has no `vocab.txt` of the real models (no network), so `synthetic_vocab` builds a seeded
 30 522-entry vocabulary with the special tokens at their real BERT ids; a real `vocab.txt` drops in

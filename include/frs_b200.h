@@ -48,7 +48,7 @@ extern "C" {
 
 #define FRS_DIM 384      /* VectorParams(size=384)  ingest.py:89-95        */
 #define FRS_MAX_BATCH 32 /* MAX_BATCH_SIZE          main2.py:51            */
-#define FRS_MAX_K 16     /* limit=15                main.py:215            */
+#define FRS_MAX_K 32     /* largest limit; the reference asks for 15 (main.py:215) and 5 (evaluate.py:86) */
 
 /* storage / arithmetic modes of the chunk store */
 #define FRS_DTYPE_F32 0  /* rows kept in fp32, TF32 tensor-core pre-filter + fp64 rescoring */
@@ -196,7 +196,7 @@ int frs_merge_shards_packed(int device, const int64_t* dev_packed, int n_shards,
 
 /* Cross-shard exchange over NVLink peer memory (replaces the all-gather of the sharded search; the reference
  * has one Qdrant server and no counterpart, main.py:215-239).  One process per GPU: every rank creates an exchange
- * (nq_max <= 32, k_max <= 16: ONE exchange serves every batch size and limit up to those), the 128-byte handles
+ * (nq_max <= 32, k_max <= 32: ONE exchange serves every batch size and limit up to those), the 128-byte handles
  * (two CUDA IPC handles) are all-gathered by the host, frs_exchange_connect maps the peers' buffers.
  * Per batch: the local pass pushes this rank's exact top-k into every peer's gather buffer and publishes a
  * sequence number (fused into the merge kernel: frs_index_search_push / frs_index_search_async /

@@ -5,13 +5,18 @@ Arithmetic: bf16 operands and activations, fp32 accumulation / LayerNorm / softm
 Tolerances (north_star: "1e-2 absolute for bf16"):
     embedding components (unit-norm rows, |x| ~ 0.05)   <= 1e-2 absolute  (measured ~1e-3)
     cosine(ours, oracle) per text                        >= 0.999
-    reranker logits                                       <= 0.12 absolute, <= 0.035 on average, on logits
-                                                          spread over [-2, 2]: six layers of bf16 activations
-                                                          leave ~5e-3 on the pooled [CLS] vector and the
-                                                          synthetic classifier (|w| ~ 0.25 x 384) amplifies it.
-                                                          The 1e-2 bound north_star quotes as an example
-                                                          for bf16 is met by embeddings and cosine scores,
-                                                          not by this head; measured values are printed.
+    reranker logits                                       <= 1.5e-2 * ||w_c||_2 absolute, <= 0.7e-2 * ||w_c||_2 on average
+                                                          (w_c = the 384-wide classifier row).  The pooler's tanh
+                                                          outputs — unit-scale, like cosine scores — carry ~5e-3 of
+                                                          zero-mean bf16 rounding noise after six layers of bf16
+                                                          activations (inside north_star's 1e-2); the classifier sums
+                                                          384 of them, so the logit noise is ||w_c||_2 times that.
+                                                          For the synthetic head (|w| ~ 0.25: ||w_c||_2 = 4.9, logits
+                                                          spread over [-2, 2]) that is 0.074 / 0.034; measured 0.05 /
+                                                          0.025, zero mean (scripts/logit_err.py).  The head itself
+                                                          runs in fp32 from fp32 [CLS] rows (it was 0.12 when it read
+                                                          the bf16-rounded row); the order of well-separated logits —
+                                                          what rerank_documents uses — is asserted to be the oracle's.
     per-stage activations of one layer                    <= 0.05 absolute on O(1) values
 fp32 mode (precision="fp32": fp32 weights, activations and FFMA arithmetic, no tensor cores), north_star "1e-5":
     embedding components <= 1e-5, last hidden state <= 1e-4 on O(5) values, reranker logits <= 1e-4
@@ -185,12 +190,15 @@ def test_reranker_logits_match_oracle(ce):
     ref = eo.score_pairs(MINILM_L6_CE, w, ids, tts, cu)
     err = np.abs(got - ref)
     print(f"logits: range [{ref.min():.2f}, {ref.max():.2f}] max err {err.max():.4f} mean err {err.mean():.4f}")
-    assert err.max() <= 0.12 and err.mean() <= 0.035
-    # rerank_documents (main.py:246): the order the reference derives from the logits
-    top = eo.rerank(ref[:15], 5)
-    gap = np.sort(ref[:15])[::-1]
-    if np.min(gap[:5] - gap[1:6]) > 0.1:
-        assert np.array_equal(eo.rerank(got[:15], 5), top)
+    wc_norm = float(np.linalg.norm(w["classifier.weight"]))
+    assert err.max() <= 1.5e-2 * wc_norm and err.mean() <= 0.7e-2 * wc_norm, (err.max(), err.mean(), wc_norm)
+    # rerank_documents (main.py:246): the order the reference derives from the logits.  Every pair of candidates whose
+    # oracle logits differ by more than twice the tolerance must come out in the oracle's order.
+    tol = 1.5e-2 * wc_norm
+    for i in range(15):
+        for j in range(15):
+            if ref[i] - ref[j] > 2 * tol:
+                assert got[i] > got[j], (i, j, ref[i], ref[j], got[i], got[j])
 
 
 def test_token_types_matter(ce):
@@ -285,8 +293,9 @@ def test_text_surface_embedder_and_reranker_follow_the_reference_contract():
     s = rr.predict(pairs)
     assert s.shape == (3,) and s.dtype == np.float32
     pi, pt, pc = tok.pack_pairs(pairs)
-    ref = eo.score_pairs(MINILM_L6_CE, synthetic_checkpoint(MINILM_L6_CE, Reranker.SYNTHETIC_SEED), pi, pt, pc)
-    assert np.abs(s - ref).max() <= 0.12
+    wce = synthetic_checkpoint(MINILM_L6_CE, Reranker.SYNTHETIC_SEED)
+    ref = eo.score_pairs(MINILM_L6_CE, wce, pi, pt, pc)
+    assert np.abs(s - ref).max() <= 1.5e-2 * float(np.linalg.norm(wce["classifier.weight"]))
     assert rr.predict([]).shape == (0,)
     rr.close()
 
@@ -331,32 +340,41 @@ def test_bf16_path_deviates_from_the_fp32_path_by_rounding_only(bge):
     assert np.abs(a - b).max() <= 1e-2 and ((a * b).sum(1)).min() >= 0.999
 
 
-@pytest.mark.parametrize("kind", ["outlier_dim", "large_offset"])
-def test_layernorm_epilogue_survives_outlier_dimensions_and_large_offsets(kind):
-    """Real BERT checkpoints have outlier hidden dimensions (one LayerNorm gain tens of times the others) and rows
-    whose mean is far from zero.  The fused ResLN epilogue keeps SHIFTED single-pass statistics; this checks it on
-    weights built to break E[x^2] - mean^2: a 50x gain on one dimension of every LayerNorm, or a +30 bias on all."""
+@pytest.mark.parametrize("kind", ["plain", "offset_300", "outlier_dim"])
+def test_resln_epilogue_statistics_are_exact_under_large_offsets_and_outliers(kind):
+    """The fused bias + residual + LayerNorm epilogue, isolated: a 1-layer model leaves the FFN-down GEMM's operands
+    (h, the residual x1) in the workspace, and the fp32 [CLS] rows come straight out of that epilogue.  Recomputing
+    LayerNorm(h . W2^T + b2 + x1) in fp64 from those very operands must give the same unit vectors to ~1e-5 — also
+    when every row sits at 300 +- 2 (E[x^2] - mean^2 would lose two to three digits of the variance there: the
+    statistics are shifted) and when one dimension is 50x the others (real checkpoints have such dimensions)."""
     from financial_rag_system_b200.checkpoint import BertShape, synthetic_checkpoint
     from financial_rag_system_b200.encoder import BertEncoder
-    from oracle import encoder_oracle as eo
+    from oracle import search_oracle as so
 
-    shape = BertShape(layers=3, has_head=False)
-    w = synthetic_checkpoint(shape, 77)
-    for name in list(w):
-        if name.endswith("LayerNorm.weight") and kind == "outlier_dim":
-            w[name] = w[name].copy()
-            w[name][17] *= 50.0
-        if name.endswith("LayerNorm.bias") and kind == "large_offset":
-            w[name] = (w[name] + 30.0).astype(np.float32)
-    ids, _, cu = _random_batch([64, 300, 9, 128], 5)
+    shape = BertShape(layers=1, has_head=False)
+    w = synthetic_checkpoint(shape, 78)
+    pre = "encoder.layer.0."
+    if kind == "offset_300":
+        w[pre + "attention.output.LayerNorm.bias"] = (w[pre + "attention.output.LayerNorm.bias"] + 300.0).astype(np.float32)
+        w[pre + "output.dense.weight"] = (w[pre + "output.dense.weight"] * 0.01).astype(np.float32)
+    if kind == "outlier_dim":
+        g = w[pre + "attention.output.LayerNorm.weight"].copy()
+        g[17] *= 50.0
+        w[pre + "attention.output.LayerNorm.weight"] = g
+    lens = [8] * 40 + [133, 5, 64]
+    ids, _, cu = _random_batch(lens, 6)
     enc = BertEncoder(shape, w, device=0, max_tokens=1024)
-    got = enc.embed_packed(ids, cu, 0)
-    hid = enc.last_hidden(int(cu[-1])).cpu().numpy()
+    got = enc.embed_packed(ids, cu, 0).astype(np.float64)             # unit([CLS] row of the layer output), fp32 path
+    starts = np.concatenate([[0], np.cumsum([(n + 7) // 8 * 8 for n in lens])])[:-1]
+    R = int(starts[-1]) + 8
+    h = enc.debug_read(5, R * 1536).cpu().numpy().reshape(R, 1536)[starts].astype(np.float64)
+    x1 = enc.debug_read(1, R * 384).cpu().numpy().reshape(R, 384)[starts].astype(np.float64)
     enc.close()
-    ref = eo.embed(shape, w, ids, cu, "cls")
-    ref_h = eo.last_hidden_packed(shape, w, ids, cu)
-    rel = np.abs(hid - ref_h).max() / np.abs(ref_h).max()
-    print(f"{kind}: |hidden| up to {np.abs(ref_h).max():.1f}, max rel err {rel:.4f}, embedding max err {np.abs(got - ref).max():.2e}, "
-          f"min cos {(got * ref).sum(1).min():.6f}")
-    assert (got * ref).sum(1).min() >= 0.999
-    assert rel <= 0.02
+    w2 = so.round_to_bf16(w[pre + "output.dense.weight"]).astype(np.float64)   # GEMM weights are kept in bf16
+    a = h @ w2.T + w[pre + "output.dense.bias"].astype(np.float64) + x1
+    mu, var = a.mean(1, keepdims=True), a.var(1, keepdims=True)
+    y = (a - mu) / np.sqrt(var + shape.ln_eps) * w[pre + "output.LayerNorm.weight"] + w[pre + "output.LayerNorm.bias"]
+    want = y / np.linalg.norm(y, axis=1, keepdims=True)
+    err = np.abs(got - want).max()
+    print(f"{kind}: pre-LN rows mean {mu.mean():.1f} std {np.sqrt(var).mean():.2f}; max |unit row - fp64| = {err:.2e}")
+    assert err <= 5e-5

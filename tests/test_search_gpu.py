@@ -62,7 +62,8 @@ def _data(n, seed, tickers=5, clustered=False):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "f32"])
-@pytest.mark.parametrize("n,nq,k", [(1, 1, 1), (100, 7, 15), (1000, 32, 15), (4097, 32, 16), (50_000, 32, 15), (200_000, 13, 5)])
+@pytest.mark.parametrize("n,nq,k", [(1, 1, 1), (100, 7, 15), (1000, 32, 15), (4097, 32, 16), (50_000, 32, 15), (200_000, 13, 5),
+                                    (4097, 32, 32), (50_000, 9, 20), (300_000, 32, 32)])
 def test_parity_sizes(dtype, n, nq, k):
     x, codes, g = _data(n, 100 + n)
     ix = _index(n, dtype)
@@ -220,7 +221,7 @@ def test_empty_index_and_argument_errors():
     with pytest.raises(ValueError):
         ix.search(np.ones((33, 384), np.float32), [0] * 33, [ANY] * 33, 15)
     with pytest.raises(ValueError):
-        ix.search(np.ones((1, 384), np.float32), [0], [ANY], 17)
+        ix.search(np.ones((1, 384), np.float32), [0], [ANY], 33)
     with pytest.raises(FrsError):
         ix.add(np.ones((101, 384), np.float32))          # over capacity
     ix.close()
