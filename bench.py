@@ -200,7 +200,7 @@ def run_reference(args):
     qps = NQ / (t * scale)
     line = {
         "impl": "reference", "metric": METRIC,
-        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup + 1,
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "probe_steps": 1,
         "ms_per_step": t * scale * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus, "self"),
@@ -252,14 +252,30 @@ class Ctx:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            # one slice of the host cores per rank: a 150 us GPU step leaves no room for the ranks' threads to migrate
+            # over each other (a 1 ms stall of ONE rank's submitting thread stalls all eight: the ranks exchange results
+            # every batch)
+            try:
+                cores = sorted(os.sched_getaffinity(0))
+                per = len(cores) // self.world
+                if per >= 2:
+                    os.sched_setaffinity(0, cores[self.local_rank * per:(self.local_rank + 1) * per])
+            except OSError:
+                pass
             os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")  # NCCL is set-up / barrier plumbing only
             dist.init_process_group("nccl", device_id=self.dev)
             self._tiny = torch.zeros(1, device=self.dev)
+            self._host_group = dist.new_group(backend="gloo")  # a barrier that keeps the waiting ranks' GPUs idle
 
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize(self.dev)
+
+    def host_barrier(self):
+        """CPU-only rendezvous (gloo): an NCCL barrier would park a spinning kernel on every waiting rank's GPU."""
+        if self.world > 1:
+            self.dist.barrier(group=self._host_group)
 
     def aligned_start(self):
         """After the host barrier: a device-side rendezvous enqueued right before the start event, so that every
@@ -375,10 +391,16 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     qd, qc, qm = dq
     peer = sh._peer if sh is not None else None
 
+    # result buffers are recycled like a serving loop would (16 batches deep: far more than are ever in flight)
+    ring = [(torch.empty((NQ, K), dtype=torch.int64, device=cx.dev), torch.empty((NQ, K), dtype=torch.float32, device=cx.dev))
+            for _ in range(16)]
+    turn = [0]
+
     def step():
         if tiles_dev is not None:
             return ix.search_tiles(qd, qc, qm, K, tiles_dev)
-        return ix.search_async(qd, qc, qm, K, exchange=peer)
+        turn[0] = (turn[0] + 1) & 15
+        return ix.search_async(qd, qc, qm, K, exchange=peer, out=ring[turn[0]])
 
     def drain():
         if tiles_dev is None:
@@ -495,6 +517,51 @@ def secondary_search(cx, rows, dtype, steps, peak):
             "note": "fp32 rows: TF32 tensor-core pre-filter + fp64 rescoring; bound = HBM at 1540 B/row" if dtype == "f32" else "bf16 rows: 772 B/row"}
 
 
+def single_process_multi_gpu(cx, steps, ref_ids, ref_scores):
+    """frs_sharded_* (ONE process driving all N GPUs, the form the reference's single server process would hold): the
+    same 10M-row corpus placed block-cyclically over the N GPUs by rank 0 alone, the same batch through the host entry
+    point; ids / scores must equal the multi-process result.  The other ranks idle at a barrier meanwhile."""
+    from financial_rag_system_b200.multigpu import MultiGpuIndex
+
+    torch = cx.torch
+    mg = MultiGpuIndex(TOTAL_ROWS, dtype="bf16", devices=list(range(cx.world)))
+    cent = bd.centroids_torch(cx.dev)
+    cdf = torch.from_numpy(bd.zipf_cdf()).to(cx.dev)
+    t0 = time.perf_counter()
+    chunk = 1 << 18
+    for s in range(0, TOTAL_ROWS, chunk):
+        m = min(chunk, TOTAL_ROWS - s)
+        x, codes = bd.rows_torch(s, m, cx.dev, cent=cent, cdf=cdf)
+        mg.add_device(x, codes)   # block by block to the shards' GPUs over NVLink, no host round trip
+    build_s = time.perf_counter() - t0
+    q, t, m = bd.queries_np("self", NQ)
+    qc, qm = t.astype(np.uint32), m.astype(np.uint32)
+
+    def run(n_steps, depth):
+        inflight, res = [], None
+        for _ in range(n_steps):
+            inflight.append(mg.submit(q, qc, qm, K))
+            if len(inflight) >= depth:
+                res = mg.collect(inflight.pop(0))
+        while inflight:
+            res = mg.collect(inflight.pop(0))
+        return res
+
+    run(5, E2E_DEPTH)
+    t0 = time.perf_counter()
+    ids, scores = run(steps, E2E_DEPTH)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    run(min(steps, 50), 1)
+    dt1 = (time.perf_counter() - t0) / min(steps, 50)
+    same = bool(np.array_equal(ids, ref_ids) and np.array_equal(scores, ref_scores))
+    mg.close()
+    return {"entry_point": "frs_sharded_search_host_submit/_collect (one process, one host thread, all GPUs)", "n_gpus": cx.world,
+            "rows": TOTAL_ROWS, "e2e_qps": NQ * steps / dt, "in_flight": E2E_DEPTH, "one_at_a_time_qps": NQ / dt1,
+            "equals_multi_process_result": same, "build_s": build_s,
+            "note": "host-timed (numpy in, numpy out); the host thread issues every GPU's copies and kernels itself"}
+
+
 def run_ours(args):
     cx = Ctx(args)
     torch = cx.torch
@@ -548,6 +615,8 @@ def run_ours(args):
         secondary["queries"] = qsets
         if cx.world == 8:
             # BASELINE.json configs[3] / the north-star target: 100M rows over 8 GPUs
+            sh.close()   # (the exchange first: it drains the index's pipelined searches)
+            sh = None
             ix.close()
             ix = None
             torch.cuda.empty_cache()
@@ -586,6 +655,23 @@ def run_ours(args):
                 secondary["embed"] = bench_encoders.measure_compact(cx, "embed", ClockSampler, summarize_clocks)
             except Exception as e:  # noqa: BLE001
                 secondary["embed"] = {"error": f"{type(e).__name__}: {e}"}
+        if cx.world > 1:
+            # the single-process multi-GPU entry points on the same GPUs: rank 0 drives all of them, the others wait
+            if sh is not None:
+                sh.close()
+                sh = None
+            if ix is not None:
+                ix.close()
+                ix = None
+            torch.cuda.empty_cache()
+            cx.barrier()
+            cx.host_barrier()
+            if cx.rank == 0:
+                try:
+                    secondary["single_process"] = single_process_multi_gpu(cx, sec_steps, r["ids"].cpu().numpy(), r["scores"].cpu().numpy())
+                except Exception as e:  # noqa: BLE001
+                    secondary["single_process"] = {"error": f"{type(e).__name__}: {e}"}
+            cx.host_barrier()  # (the other ranks wait on the host: their GPUs are rank 0's to use meanwhile)
 
     if cx.rank == 0:
         traffic = None

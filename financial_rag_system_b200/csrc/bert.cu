@@ -787,19 +787,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // register file is re-divided at kernel start (setmaxnreg): 64 per thread for warpgroup 0, 216 for the
 // softmax warpgroups.  P goes back to tensor memory (the A operand of P.V) and O stays there for the whole
 // item; see the softmax branch for the lazy reference maximum and the turn-taking of the two heads.
-constexpr int kAttnThreads = 384;
-constexpr int kAttnRegsLow = 64;
-constexpr int kAttnRegsHigh = 216;
-constexpr int kKB = 128;              // keys per block
+// Two builds of the kernel (-DFRS_ATTN_KB=128 | 64):
+//   128 keys per block, one role set per CTA (384 threads): a softmax thread holds a 128-score row (216 registers) —
+//     the default;
+//   64 keys per block, TWO independent role sets ("groups") in one 768-thread CTA: each group is the complete
+//     384-thread machine — its own TMA producer, MMA issuer, eight softmax warps, its own shared-memory ring,
+//     mbarriers and half of the CTA's tensor memory — working on its own items; with 64-key blocks a softmax thread
+//     needs 104 registers, so both groups fit the register file.  Each SM sub-partition then hosts FOUR softmax warps
+//     that are not synchronised with each other.  The idea was to keep the MUFU busy while a warp is in its load /
+//     max / pack phases (one group per SM: 59-68 % MUFU utilisation).  MEASURED (B200, 128 x 512 tokens): 2.20 ms of
+//     attention per 12-layer pass against 1.74 ms for the 128-key build — twice as many blocks means twice the
+//     per-block fixed work (TMEM round trips, barrier hand-offs, P.V issue), the 104-register softmax threads and
+//     the 32-register issuer spill, and nothing is left of the MUFU gain.  Parity-clean, kept as a build option.
+//     Why not simply two CTAs per SM: a kernel that allocates tensor memory is limited to ONE resident CTA per SM
+//     (scripts/micro/occ_probe.cu: cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1 as soon as tcgen05.alloc appears,
+//     whatever the registers and shared memory; measured: the 2-CTA build ran exactly as fast as one CTA).
+#ifndef FRS_ATTN_KB
+#define FRS_ATTN_KB 128
+#endif
+constexpr int kKB = FRS_ATTN_KB;      // keys per block
+static_assert(kKB == 64 || kKB == 128, "key block is 64 or 128 keys");
+constexpr int kAttnGroups = kKB == 64 ? 2 : 1;
+constexpr int kAttnGroupThreads = 384;
+constexpr int kAttnThreads = kAttnGroupThreads * kAttnGroups;
+constexpr int kAttnRegsLow = kKB == 64 ? 32 : 64;   // per group 128 x low + 256 x high must fit what it was launched with (384 x 80 | 384 x 168)
+constexpr int kAttnRegsHigh = kKB == 64 ? 104 : 216;
 constexpr int kKVStages = 4;
 constexpr int kQBytes = kBM * 128;            // 128 queries x 64 dims
-constexpr int kKBytes = kKB * 128;            // 128 keys x 64 dims
+constexpr int kKBytes = kKB * 128;            // kKB keys x 64 dims
 constexpr int kVSlab = 64 * 128;              // 64 dims x 64 keys
-constexpr int kVBytes = 2 * kVSlab;           // 128 keys
+constexpr int kVSlabs = kKB / 64;
+constexpr int kVBytes = kVSlabs * kVSlab;     // kKB keys
 constexpr int kKVBytes = kKBytes + kVBytes;
-constexpr int kTmemS = 0;                     // TMEM columns: S of head h at [128h, +128)
-constexpr int kTmemO = 256;                   //   O block of head h at [256 + 32h, +32)
-constexpr int kTmemP = 320;                   //   P of head h (bf16 pairs) at [320 + 64h, +64)
+constexpr int kTmemCols = 4 * kKB;            // 512 | 256 (a power of two)
+constexpr int kTmemS = 0;                     // TMEM columns: S of head h at [kKB h, +kKB)
+constexpr int kTmemO = 2 * kKB;               //   O block of head h at [2 kKB + 32h, +32)
+constexpr int kTmemP = 2 * kKB + 64;          //   P of head h (bf16 pairs) at [2 kKB + 64 + (kKB/2) h, +kKB/2)
+static_assert(kTmemP + kKB <= kTmemCols, "TMEM budget");
 
 struct AttnSmem {
   static constexpr int q = 0;                                  // [2]
@@ -808,6 +832,7 @@ struct AttnSmem {
   static constexpr int nbars = 2 + 2 + 2 * kKVStages + 8;
   static constexpr int holder = bars + nbars * 8;
   static constexpr int total = holder + 16;
+  static constexpr int group = (total + 1023) / 1024 * 1024;   // a group's region (1024-aligned: SWIZZLE_128B tiles)
 };
 
 // -DFRS_ATTN_TRACE: event timeline (clock64 << 8 | event id) of CTA 0: role 0 = MMA issuer, role 1 / 2 = lane 0 of
@@ -819,12 +844,17 @@ constexpr int kTraceCap = 4096;
 #define FRS_TR(id) do { } while (0)
 #endif
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
-                 const AttnParams p) {
+attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the pointer in the shared address space: rounding the
   // pointer through uintptr_t made every staging access a generic LD.E / ST.E instead of LDS / STS)
-  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sm0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // role set ("group") of this thread: everything below is per group — shared-memory region, barriers, TMEM half, items
+  const uint32_t grp = threadIdx.x / kAttnGroupThreads;
+  const uint32_t gtid = threadIdx.x - grp * kAttnGroupThreads;
+  uint8_t* sm = sm0 + grp * AttnSmem::group;
+  const int item0 = (int)(blockIdx.x * kAttnGroups + grp), item_step = (int)(gridDim.x * kAttnGroups);
   uint64_t* q_full = reinterpret_cast<uint64_t*>(sm + AttnSmem::bars);
   uint64_t* q_empty = q_full + 2;
   uint64_t* kv_full = q_empty + 2;
@@ -833,13 +863,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
   uint64_t* s_free = s_full + 2;
   uint64_t* p_full = s_free + 2;
   uint64_t* o_full = p_full + 2;
-  uint32_t* holder = reinterpret_cast<uint32_t*>(sm + AttnSmem::holder);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(sm0 + AttnSmem::holder);  // (group 0's: one allocation for the CTA)
 
-  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t warp = gtid >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const int n_items = p.nqb * kHeadPairs;
 
-  if (threadIdx.x == 0) {
+  if (gtid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
@@ -854,23 +884,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(holder, 512);
+  if (warp == 1 && grp == 0) {
+    tmem_alloc(holder, kTmemCols * kAttnGroups);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *holder;
+  const uint32_t tmem_base = *holder + grp * kTmemCols;
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAttnRegsLow));
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&tmap_qk);
+      tma_prefetch_desc(&tmap_k);
       tma_prefetch_desc(&tmap_vt);
       uint32_t li = 0, g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+      for (int item = item0; item < n_items; item += item_step, ++li) {
         const QBlock qb = p.qblk[item / kHeadPairs];
         const int hp = item % kHeadPairs;
         const uint32_t qbuf = li & 1;
@@ -884,9 +915,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           mbar_arrive_expect_tx(&kv_full[stage], kKVBytes);
           uint8_t* dst = sm + AttnSmem::kv + (size_t)stage * kKVBytes;
           const int tok = qb.kv_tok0 + kb * kKB;
-          tma_load_2d(dst, &tmap_qk, &kv_full[stage], kHid + hp * 64, tok, kEvictNormal);
-          tma_load_2d(dst + kKBytes, &tmap_vt, &kv_full[stage], tok, hp * 64, kEvictNormal);
-          tma_load_2d(dst + kKBytes + kVSlab, &tmap_vt, &kv_full[stage], tok + 64, hp * 64, kEvictNormal);
+          tma_load_2d(dst, &tmap_k, &kv_full[stage], kHid + hp * 64, tok, kEvictNormal);  // box of kKB key rows
+#pragma unroll
+          for (int sl = 0; sl < kVSlabs; ++sl)
+            tma_load_2d(dst + kKBytes + sl * kVSlab, &tmap_vt, &kv_full[stage], tok + 64 * sl, hp * 64, kEvictNormal);
         }
       }
     }
@@ -922,7 +954,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         ++c.g;
         if (++c.kb == c.nkb) {
           c.kb = 0;
-          c.item += gridDim.x;
+          c.item += item_step;
           ++c.li;
           load_item(c);
         }
@@ -941,13 +973,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           FRS_TR(1 + h);
           const uint64_t da = make_desc_sw128(q_addr) + 4 * h;  // +64 bytes: second head of the pair
           const uint64_t db = make_desc_sw128(k_addr) + 4 * h;
-          tc_mma_f16_pred(tmem_u + kTmemS + 128 * h, da, db, idesc_s, 0u, issue);
-          tc_mma_f16_pred(tmem_u + kTmemS + 128 * h, da + 2, db + 2, idesc_s, 1u, issue);
+          tc_mma_f16_pred(tmem_u + kTmemS + kKB * h, da, db, idesc_s, 0u, issue);
+          tc_mma_f16_pred(tmem_u + kTmemS + kKB * h, da + 2, db + 2, idesc_s, 1u, issue);
           tc_commit_pred(&s_full[h], issue);
           FRS_TR(3 + h);
         }
       };
-      Cursor cs{(int)blockIdx.x, 0, 0, 0u, 0u}, cp{(int)blockIdx.x, 0, 0, 0u, 0u};
+      Cursor cs{item0, 0, 0, 0u, 0u}, cp{item0, 0, 0, 0u, 0u};
       load_item(cs);
       load_item(cp);
       if (cs.item < n_items) {
@@ -967,11 +999,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           tc_fence_after();
           FRS_TR(5 + h);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < kVSlabs; ++s) {
             const uint64_t db = make_desc_sw128(v_addr + s * kVSlab + h * (kHeadDim * 128));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)  // 16 keys per MMA = 8 columns of packed bf16 pairs
-              tc_mma_ts_pred(tmem_u + kTmemO + 32 * h, tmem_u + kTmemP + 64 * h + (s * 4 + kk) * 8, db + 2 * kk,
+              tc_mma_ts_pred(tmem_u + kTmemO + 32 * h, tmem_u + kTmemP + (kKB / 2) * h + (s * 4 + kk) * 8, db + 2 * kk,
                              idesc_o, (uint32_t)((cp.kb | s | kk) != 0), issue);
           }
           tc_commit_pred(&o_full[h], issue);
@@ -989,9 +1021,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     const uint32_t quarter = warp & 3;
     const uint32_t h = (warp >> 2) - 1;
     const uint32_t row = quarter * 32 + lane;
-    const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + kTmemS + 128 * h;
+    const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + kTmemS + kKB * h;
     const uint32_t t_o = tmem_base + ((quarter * 32u) << 16) + kTmemO + 32 * h;
-    const uint32_t t_p = tmem_base + ((quarter * 32u) << 16) + kTmemP + 64 * h;
+    const uint32_t t_p = tmem_base + ((quarter * 32u) << 16) + kTmemP + (kKB / 2) * h;
     uint32_t g = 0;
 #ifdef FRS_ATTN_TRACE
     long long* tr = (p.timing && blockIdx.x == 0 && quarter == 0 && lane == 0) ? p.timing + 64 + (1 + h) * kTraceCap : nullptr;
@@ -1019,7 +1051,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
 #endif
     constexpr float kLazyLog2 = FRS_LAZY_LOG2;  // -DFRS_LAZY_LOG2=0.f: every increase of the maximum rescales (exercises the rare path)
     float m = -INFINITY, l = 0.f;
-    QBlock qb_next = p.qblk[(blockIdx.x < n_items ? blockIdx.x : 0) / kHeadPairs];
+    QBlock qb_next = p.qblk[(item0 < n_items ? item0 : 0) / kHeadPairs];
     __nv_bfloat16* dst_prev = nullptr;  // context row of this thread in the item being accumulated (null: padding row)
     // writes the context row of the item that ended with block g - 1 (its accumulated O is in TMEM)
     auto flush_item = [&]() {
@@ -1045,13 +1077,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
       FRS_T(7);
       FRS_TR(20);
     };
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
       const QBlock qb = qb_next;
-      if (item + (int)gridDim.x < n_items) qb_next = p.qblk[(item + gridDim.x) / kHeadPairs];
+      if (item + item_step < n_items) qb_next = p.qblk[(item + item_step) / kHeadPairs];
       const int hp = item % kHeadPairs;
       const int key_off = qb.seq_tok0 - qb.kv_tok0;  // keys of the first block before the sequence (< 8)
       const int nkb = (key_off + qb.seq_len + kKB - 1) / kKB;
-      uint32_t s0[32], s1[32], s2[32], s3[32];  // one score row of the block: a single pass over TMEM
+      constexpr int kSC = kKB / 32;  // 32-score chunks of a row
+      uint32_t sc[kSC][32];          // one score row of the block: a single pass over TMEM (all indices are static)
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         // keys [lo, hi) of this block belong to the sequence (hi - lo >= 1)
         const int lo = kb == 0 ? key_off : 0;
@@ -1063,10 +1096,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         tc_fence_after();
         FRS_T(1);
         FRS_TR(11);
-        tmem_ld_32x32(t_s, s0);
-        tmem_ld_32x32(t_s + 32, s1);
-        tmem_ld_32x32(t_s + 64, s2);
-        tmem_ld_32x32(t_s + 96, s3);
+#pragma unroll
+        for (int c = 0; c < kSC; ++c) tmem_ld_32x32(t_s + 32 * c, sc[c]);
         tmem_ld_wait();
         // S is in registers: the MMA warp may already compute the next block's scores into it
         tc_fence_before();
@@ -1080,21 +1111,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j < lo || c * 32 + j >= hi) sv[j] = 0xff800000u;  // -inf
           };
-          mask(s0, 0);
-          mask(s1, 1);
-          mask(s2, 2);
-          mask(s3, 3);
+#pragma unroll
+          for (int c = 0; c < kSC; ++c) mask(sc[c], c);
         }
         // block maximum (scores are already in the log2 domain: q was scaled by log2e/sqrt(32))
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        float mx[kSC];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {  // FMNMX3: two scores per instruction
-          mx0 = fmax3(mx0, __uint_as_float(s0[j]), __uint_as_float(s0[j + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(s1[j]), __uint_as_float(s1[j + 1]));
-          mx2 = fmax3(mx2, __uint_as_float(s2[j]), __uint_as_float(s2[j + 1]));
-          mx3 = fmax3(mx3, __uint_as_float(s3[j]), __uint_as_float(s3[j + 1]));
+        for (int c = 0; c < kSC; ++c) mx[c] = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {  // FMNMX3: two scores per instruction, kSC independent chains
+#pragma unroll
+          for (int c = 0; c < kSC; ++c) mx[c] = fmax3(mx[c], __uint_as_float(sc[c][j]), __uint_as_float(sc[c][j + 1]));
         }
-        const float bm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        float bm = mx[0];
+#pragma unroll
+        for (int c = 1; c < kSC; ++c) bm = fmaxf(bm, mx[c]);
         FRS_T(3);
         FRS_TR(13);
         bool pv_done = g == 0;  // P.V of block g - 1 is known to have finished (its P buffer may be overwritten)
@@ -1142,17 +1173,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         // P goes straight back to tensor memory as the A operand of P.V: key k of this row = half (k & 1) of
         // column k / 2.  It never touches shared memory.
         float ps0 = 0.f, ps1 = 0.f;
-        uint32_t pw0[32], pw1[32];  // two buffers: the asynchronous TMEM store of the first may still read it
+        constexpr int kPairs = kKB / 2;  // score pairs = packed P words of a row
+        uint32_t pw[kPairs / 16][16];    // stored 16 words at a time; a chunk is not reused while its asynchronous store may read it
 #ifndef FRS_ATTN_NO_TURNS
         // The two warps of a sub-partition (same quarter, head 0 / head 1) share one MUFU unit.  Left alone
         // they run in lockstep (both are released by the same score MMAs): both exponentiate at half rate,
         // then both leave the unit idle.  They take turns instead, so that the exp pass of one head overlaps
         // the load / max phases of the other.  The float operand ties the barrier into the data flow: no exp
         // may be scheduled above it.
-        if (h == 0) {
-          if (g > 0) asm volatile("bar.sync %1, 64;" : "+f"(m) : "r"(5u + quarter) : "memory");
-        } else {
-          asm volatile("bar.sync %1, 64;" : "+f"(m) : "r"(1u + quarter) : "memory");
+        // (Only with ONE group per CTA: with two, four unsynchronised warps share the unit and need no turns — and
+        // the second group's barriers would not fit the 16 named barriers of a CTA.)
+        if constexpr (kAttnGroups == 1) {
+          if (h == 0) {
+            if (g > 0) asm volatile("bar.sync %1, 64;" : "+f"(m) : "r"(5u + quarter) : "memory");
+          } else {
+            asm volatile("bar.sync %1, 64;" : "+f"(m) : "r"(1u + quarter) : "memory");
+          }
         }
 #endif
         FRS_TR(16);
@@ -1165,10 +1201,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
 #define FRS_ATTN_FMA_OF4 0
 #endif
         constexpr int kExpFmaOf4 = FRS_ATTN_FMA_OF4;
+        // The other head's warp is released when this pass has issued kArriveAt of its 64 score pairs, not at its
+        // end: the tail of this pass then interleaves with the head of the other one on the shared MUFU (two warps
+        // in the pass at once saturate the unit; one alone leaves it idle during its FADD2 / pack instructions).
+#ifndef FRS_ATTN_ARRIVE_AT
+#define FRS_ATTN_ARRIVE_AT kPairs
+#endif
+        constexpr int kArriveAt = FRS_ATTN_ARRIVE_AT;
 #pragma unroll
-        for (int j = 0; j < 64 + kExpLag; ++j) {
-          if (j < 64) {
-            uint32_t(&sv)[32] = j < 16 ? s0 : j < 32 ? s1 : j < 48 ? s2 : s3;
+        for (int j = 0; j < kPairs + kExpLag; ++j) {
+#ifndef FRS_ATTN_NO_TURNS
+          if (kAttnGroups == 1 && kArriveAt > 0 && kArriveAt < kPairs && j == kArriveAt) {
+            // tied to the last exponential issued (a score register) and to m (every later FADD2 reads it)
+            asm volatile("bar.arrive %2, 64;" : "+f"(m), "+r"(sc[(j - 1) >> 4][((j - 1) & 15) * 2 + 1]) : "r"((h == 0 ? 1u : 5u) + quarter) : "memory");
+          }
+#endif
+          if (j < kPairs) {
+            uint32_t(&sv)[32] = sc[j >> 4];
             const int i = (j & 15) * 2;
             float a = __uint_as_float(sv[i]), b = __uint_as_float(sv[i + 1]);
             fadd2(a, b, -m, -m);  // FADD2: one issue slot per score pair
@@ -1187,17 +1236,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           }
           if (j >= kExpLag) {
             const int jj = j - kExpLag;
-            uint32_t(&sv)[32] = jj < 16 ? s0 : jj < 32 ? s1 : jj < 48 ? s2 : s3;
+            uint32_t(&sv)[32] = sc[jj >> 4];
             const int i = (jj & 15) * 2;
             const float a = __uint_as_float(sv[i]), b = __uint_as_float(sv[i + 1]);
             fadd2(ps0, ps1, a, b);
-            (jj < 32 ? pw0 : pw1)[jj & 31] = pack_bf16x2(a, b);
-            if (jj == 31) tmem_st_32x32(t_p, pw0);
+            pw[jj >> 4][jj & 15] = pack_bf16x2(a, b);
+            if ((jj & 15) == 15) tmem_st_32x16(t_p + 16 * (jj >> 4), pw[jj >> 4]);
           }
         }
-        tmem_st_32x32(t_p + 32, pw1);
 #ifndef FRS_ATTN_NO_TURNS
-        asm volatile("bar.arrive %2, 64;" : "+f"(ps0), "+f"(ps1) : "r"((h == 0 ? 1u : 5u) + quarter) : "memory");
+        if (kAttnGroups == 1 && (kArriveAt <= 0 || kArriveAt >= kPairs))
+          asm volatile("bar.arrive %2, 64;" : "+f"(ps0), "+f"(ps1) : "r"((h == 0 ? 1u : 5u) + quarter) : "memory");
 #endif
         FRS_TR(17);
         l += ps0 + ps1;
@@ -1211,7 +1260,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     }
     if (g > 0) flush_item();
 #ifndef FRS_ATTN_NO_TURNS
-    if (h == 0 && g > 0) named_bar_sync(5u + quarter, 64);  // consume the last turn of head 1
+    if (kAttnGroups == 1 && h == 0 && g > 0) named_bar_sync(5u + quarter, 64);  // consume the last turn of head 1
 #endif
 #ifdef FRS_ATTN_TIMING
     if (p.timing && lane == 0 && blockIdx.x == 0)
@@ -1220,7 +1269,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1 && grp == 0) tmem_dealloc(tmem_base, kTmemCols * kAttnGroups);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1278,7 +1327,7 @@ size_t gemm_smem_bytes(int epi) {
   (void)epi;
   return GemmCfg<192, false>::kTotal + 1024;  // (both configurations are within 1 KB of each other)
 }
-size_t attn_smem_bytes() { return AttnSmem::total + 1024; }
+size_t attn_smem_bytes() { return (size_t)AttnSmem::group * kAttnGroups + 1024; }
 
 cudaError_t launch_row_map(const int32_t* cu_seqlens, const int32_t* row_start, int n_seqs, int32_t* src_tok,
                            int32_t* pos_of_row, int32_t* row_of_tok, int32_t* cls_slot, cudaStream_t st) {
@@ -1369,18 +1418,36 @@ cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const 
   }
 }
 
-cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_vt,
+int attn_key_block() { return kKB; }
+
+cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_k, const CUtensorMap& tmap_vt,
                              const AttnParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured[64] = {};
   const size_t smem = attn_smem_bytes();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (getenv("FRS_DEBUG_OCC")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attention_kernel, kAttnThreads, smem);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, attention_kernel);
+      int nb0 = 0, nb1 = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, attention_kernel, kAttnThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, attention_kernel, kAttnThreads, 64 * 1024);
+      fprintf(stderr, "[attention] %d keys per block, %zu B dynamic + %zu B static shared memory per CTA, %d registers, %d resident "
+              "CTA(s) per SM (%d role set(s) per CTA; %d with no dynamic smem, %d with 64 KB)\n", kKB, smem, fa.sharedSizeBytes, fa.numRegs, nb,
+              kAttnGroups, nb0, nb1);
+    }
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int items = p.nqb * kHeadPairs;
   if (items <= 0) return cudaSuccess;
-  const int grid = items < sm_count ? items : sm_count;
+  const int ctas = (items + kAttnGroups - 1) / kAttnGroups;  // a CTA's groups take consecutive items
+  const int grid = ctas < sm_count ? ctas : sm_count;
 #ifdef FRS_ATTN_TRACE
   {
     static long long* th = nullptr;
@@ -1390,7 +1457,7 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
     memset(th, 0, n * 8);
     AttnParams pd = p;
     cudaHostGetDevicePointer(&pd.timing, th, 0);
-    attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, pd);
+    attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_k, tmap_vt, pd);
     cudaStreamSynchronize(st);
     if (++calls == 30) {
       FILE* f = fopen("gpurun_out/attn_trace.txt", "w");
@@ -1410,7 +1477,7 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   if (!th) cudaHostAlloc(&th, 64 * 8, cudaHostAllocMapped);
   AttnParams pd = p;
   cudaHostGetDevicePointer(&pd.timing, th, 0);
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, pd);
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_k, tmap_vt, pd);
   if (++calls % 12 == 0) {
     cudaStreamSynchronize(st);
     static const char* names[8] = {"loop", "wait_s", "ld_s", "max", "wait_o", "o_upd", "exp+store", "item_tail"};
@@ -1422,7 +1489,7 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   }
   return cudaGetLastError();
 #endif
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_vt, p);
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_k, tmap_vt, p);
   return cudaGetLastError();
 }
 

@@ -89,7 +89,8 @@ cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const 
                         const CUtensorMap& tmap_out, const CUtensorMap& tmap_out2, const GemmParams& p,
                         cudaStream_t st);
 // tmap_qk: qk [rows, 768], box 64 x 128; tmap_vt: vt [384, rows], box 64 x 64; both SWIZZLE_128B
-cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_vt,
+int attn_key_block();  // keys per block of the compiled attention kernel = rows of the K tensor map's box
+cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_k, const CUtensorMap& tmap_vt,
                              const AttnParams& p, cudaStream_t st);
 // pool_mode 0 = CLS row, 1 = mean over the sequence; then x / max(||x||, 1e-12)
 cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, const int32_t* row_start,

@@ -63,6 +63,7 @@ struct frs_encoder {
   int32_t *d_cu = nullptr, *d_rs = nullptr;  // caller cu_seqlens | internal row starts (multiples of 8)
   QBlock* d_qblk = nullptr;
   CUtensorMap t_x0, t_x1, t_ctx, t_h, t_qk, t_vt;  // box 64 x 128 (vt: 64 x 64): GEMM A operands, attention loads
+  CUtensorMap t_k;  // qk with a box of attn_key_block() rows: the attention kernel's K tiles
   CUtensorMap s_x0, s_x1, s_h, s_qk, s_vt;         // epilogue stores: box 32 x 128 SWIZZLE_64B (vt: 64 tokens x 32 dims)
   // staging
   int32_t *h_cu = nullptr, *h_rs = nullptr, *h_ids = nullptr, *h_type = nullptr;
@@ -285,6 +286,7 @@ extern "C" int frs_encoder_create(int device, const frs_bert_cfg* cfg, const flo
   EN_RC(abi_make_tmap_bf16(&e->t_h, e->h, T, kFfn, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_qk, e->qk, T, 2 * kHid, 64, kBM));
   EN_RC(abi_make_tmap_bf16(&e->t_vt, e->vt, kHid, T, 64, 64));
+  EN_RC(abi_make_tmap_bf16(&e->t_k, e->qk, T, 2 * kHid, 64, (uint32_t)attn_key_block()));
   EN_RC(abi_make_tmap_bf16(&e->s_x0, e->x0, T, kHid, 32, kBM));
   EN_RC(abi_make_tmap_bf16(&e->s_x1, e->x1, T, kHid, 32, kBM));
   EN_RC(abi_make_tmap_bf16(&e->s_h, e->h, T, kFfn, 32, kBM));
@@ -413,7 +415,7 @@ static int forward(frs_encoder* e, const int32_t* d_ids, const int32_t* d_type, 
     a.qblk = e->d_qblk;
     a.nqb = nqb;
     a.ctx = e->ctx;
-    CU_TRY(launch_attention(e->sm_count, e->t_qk, e->t_vt, a, st));
+    CU_TRY(launch_attention(e->sm_count, e->t_qk, e->t_k, e->t_vt, a, st));
     if ((rc = prof_mark(e, kPAttn, st))) return rc;
     // attention output projection + residual + LayerNorm
     g.N = kHid;

@@ -310,6 +310,7 @@ extern "C" int frs_index_set_size(frs_index* idx, int64_t n) {
 // that event; every search waits on it before its first kernel, so a search whose size snapshot includes new
 // rows never reads them half-written.  An in-place overwrite additionally waits for the searches in flight.
 static int write_begin(frs_index* ix, cudaStream_t st, bool in_place) {
+  ix->writes_pending = true;
   CU_TRY(cudaStreamWaitEvent(st, ix->rows_ready, 0));
   if (in_place)
     for (SearchWs& w : ix->ws) CU_TRY(cudaStreamWaitEvent(st, w.free, 0));
@@ -502,7 +503,10 @@ int search_enqueue(frs_index* ix, const SearchArgs& a, const SearchLaunch& L) {
   const bool bracket = ix->prof_mode == 3 && ix->br_first;
   // the workspace's previous search (kWsRing calls ago) and the pending writes come first
   CU_TRY(cudaStreamWaitEvent(L.prep, w.free, 0));
-  CU_TRY(cudaStreamWaitEvent(L.prep, ix->rows_ready, 0));
+  if (ix->writes_pending) {  // (skipped while the store is read-only: one driver call less per search)
+    CU_TRY(cudaStreamWaitEvent(L.prep, ix->rows_ready, 0));
+    if (cudaEventQuery(ix->rows_ready) == cudaSuccess) ix->writes_pending = false;
+  }
   int launches = 0;
   if (pev) CU_TRY(cudaEventRecord(pev[0], L.prep));
   CU_TRY(launch_prep_queries(f32, a.q, a.code, a.mask, a.nq, w.qop, w.qrec, w.qcode, w.qmask, w.stats, w.gmax,

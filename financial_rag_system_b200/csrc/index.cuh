@@ -104,6 +104,7 @@ struct frs_index {
   cudaEvent_t job_in[frs::kJobRing], job_prep[frs::kJobRing], job_scan[frs::kJobRing], job_done[frs::kJobRing];
   uint64_t jobs = 0;
   cudaEvent_t rows_ready = nullptr;  // recorded after the last write-path kernel; every search waits on it
+  bool writes_pending = false;       // a write was issued and rows_ready has not been seen complete yet
   // profiling (off by default)
   static constexpr int kProfRing = 256;
   int prof_mode = 0;   // 0 off, 1 events, 2 events + in-kernel timeline

@@ -190,10 +190,12 @@ class VectorIndex:
 
     # -- pipelined forms (frs_index_search_async / _host_submit / _host_collect) ------------------
     def search_async(self, queries: torch.Tensor, q_code: torch.Tensor, q_mask: torch.Tensor, k: int = 15,
-                     exchange=None) -> PendingSearch:
+                     exchange=None, out=None) -> PendingSearch:
         """Pipelined search of device tensors: prep / scan / merge run on the index's internal streams, so
         consecutive calls overlap (the scans run back to back).  Inputs are read in current-stream order.
-        `exchange`: a sharded.PeerExchange — the result is then the global top-k over all ranks."""
+        `exchange`: a sharded.PeerExchange — the result is then the global top-k over all ranks.
+        `out`: optional (ids int64 [nq,k], scores float32 [nq,k]) device tensors to write into (a serving loop that
+        recycles its result buffers keeps the allocator out of the request path)."""
         q = queries
         if q.dtype != torch.float32 or q.device != self.device or not q.is_contiguous():
             q = q.to(device=self.device, dtype=torch.float32).contiguous()
@@ -201,10 +203,15 @@ class VectorIndex:
         self._check_batch(nq, k)
         qc = q_code if (q_code.dtype == torch.int32 and q_code.device == self.device) else self._as_code_tensor(q_code)
         qm = q_mask if (q_mask.dtype == torch.int32 and q_mask.device == self.device) else self._as_code_tensor(q_mask)
-        # one allocation for both outputs: [nq*k] int64 ids followed by [nq*k] float32 scores
-        buf = torch.empty(nq * k * 12, dtype=torch.uint8, device=self.device)
-        ids = buf[:nq * k * 8].view(torch.int64).view(nq, k)
-        scores = buf[nq * k * 8:].view(torch.float32).view(nq, k)
+        if out is not None:
+            ids, scores = out
+            assert ids.dtype == torch.int64 and scores.dtype == torch.float32 and tuple(ids.shape) == tuple(scores.shape) == (nq, k)
+            assert ids.is_contiguous() and scores.is_contiguous() and ids.device == scores.device == self.device
+        else:
+            # one allocation for both outputs: [nq*k] int64 ids followed by [nq*k] float32 scores
+            buf = torch.empty(nq * k * 12, dtype=torch.uint8, device=self.device)
+            ids = buf[:nq * k * 8].view(torch.int64).view(nq, k)
+            scores = buf[nq * k * 8:].view(torch.float32).view(nq, k)
         ticket = C.c_int(-1)
         check(self._lib.frs_index_search_async(self._h, exchange._h if exchange is not None else None, _ptr(q), _ptr(qc),
                                                _ptr(qm), nq, k, _ptr(scores), _ptr(ids), _stream_ptr(self.device),

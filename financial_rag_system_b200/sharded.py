@@ -295,7 +295,8 @@ class ShardedIndex:
         if self._side is not None:
             self._side.synchronize()
         if self._peer is not None:
-            self.local.sync(-1)
+            if getattr(self.local, "_h", None):   # (a local index that was closed first has nothing left to drain)
+                self.local.sync(-1)
             self._peer.close()
             self._peer = None
 
