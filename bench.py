@@ -283,6 +283,14 @@ class Ctx:
         if self.world > 1:
             self.dist.all_reduce(self._tiny)
 
+    def gather_floats(self, v):
+        if self.world == 1:
+            return [float(v)]
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
     def max_over_ranks(self, v):
         if self.world == 1:
             return float(v)
@@ -420,6 +428,10 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     if cx.rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+
+    gc.collect()
+    gc.disable()   # a collection pause of one rank's submitting thread stalls every rank (they exchange results per batch)
     cx.barrier()
     cx.aligned_start()
     e0.record()
@@ -429,11 +441,13 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     host_us = (time.perf_counter() - h0) / steps * 1e6   # host time to enqueue one step (must stay under the GPU's)
     drain()
     e1.record()
+    gc.enable()
     if cx.rank == 0:
         sampler.sample()  # the GPU is still working through the queued steps: at least one sample under load
     cx.barrier()
     samples = sampler.finish()
-    ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    ms_own = e0.elapsed_time(e1)
+    ms = cx.max_over_ranks(ms_own)
     ids, scores = (last.ids, last.scores) if tiles_dev is None else last
     bracket = ix.read_profile_ex() if tiles_dev is None else None
 
@@ -451,7 +465,7 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     stats = ix.last_stats()
     launches = stats["launches"]
 
-    out = {"host_enqueue_us_per_step": cx.max_over_ranks(host_us), "ms": ms, "ids": ids, "scores": scores, "samples": samples, "launches_per_step": launches, "stats": stats,
+    out = {"host_enqueue_us_per_step": cx.max_over_ranks(host_us), "ms_per_rank": cx.gather_floats(ms_own), "ms": ms, "ids": ids, "scores": scores, "samples": samples, "launches_per_step": launches, "stats": stats,
            "breakdown": {"prep": prof["prep_ms"] / n, "scan": prof["scan_ms"] / n, "merge": prof["merge_ms"] / n,
                          "exchange": prof["exchange_ms"] / n, "gap": prof["scan_gap_ms"] / max(n - 1, 1),
                          "step": prof["span_ms"] / n}}
@@ -708,6 +722,7 @@ def run_ours(args):
                          "whole_step_frac": r["alg_bytes"] / (ms / steps * 1e-3) / 1e9 / peak},
             "breakdown_ms": {k: round(v, 5) for k, v in r["breakdown"].items()},
             "host_enqueue_us_per_step": round(r["host_enqueue_us_per_step"], 1),
+            "timed_region_ms_per_rank": [round(v, 4) for v in r["ms_per_rank"]],
             "scan_stats_last_step": {k: r["stats"][k] for k in ("appended", "compactions", "resolutions", "rescored", "grid")},
             "parity_checked": checked, "prefilter_max_err": pre_err, "prefilter_eps": 3e-5,
             "comm": ("peer-memory stores + flags inside the merge kernel (csrc/exchange.cu); NCCL is used for process-group set-up and "

@@ -62,32 +62,6 @@ exchange_push_kernel(const uint64_t* __restrict__ local, uint64_t* const* __rest
   }
 }
 
-// one warp: lane r waits for rank r's flag.  Bounded by wall-clock time; on time-out the batch is poisoned and
-// the sequence number reported to the host — never a trap.  A poisoned exchange stays poisoned (the ranks'
-// sequence numbers can no longer be trusted): the owner destroys and re-creates it on every rank.
-__global__ void exchange_wait_kernel(const uint32_t* __restrict__ flags, int world, uint32_t seq,
-                                     unsigned long long timeout_ns, uint32_t* poison, uint32_t* status) {
-  if (*reinterpret_cast<volatile uint32_t*>(poison) != 0u) return;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (int r = threadIdx.x; r < world; r += blockDim.x) {
-    uint32_t v;
-    for (;;) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-      if ((int32_t)(v - seq) >= 0) break;
-      __nanosleep(200);
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > timeout_ns) {
-        *reinterpret_cast<volatile uint32_t*>(poison) = 1u;
-        *reinterpret_cast<volatile uint32_t*>(status) = seq;
-        __threadfence_system();
-        break;
-      }
-    }
-  }
-}
-
 void free_exchange(frs_exchange* ex) {
   for (void* p : ex->opened) cudaIpcCloseMemHandle(p);
   cudaFree(ex->gather);
@@ -136,7 +110,6 @@ extern "C" int frs_exchange_create(int device, int world, int rank, int nq_max, 
   }
   cudaFuncAttributes fa;  // load the exchange kernels now, not at their first launch (see preload_search_kernels)
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, (const void*)exchange_push_kernel);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, (const void*)exchange_wait_kernel);
   if (e == cudaSuccess) e = frs::preload_search_kernels();
   if (e == cudaSuccess) e = cudaMemset(ex->gather, 0, gbytes);
   if (e == cudaSuccess) e = cudaMemset(ex->flags, 0, (size_t)world * 4);
@@ -277,11 +250,10 @@ void exchange_commit_push(frs_exchange* ex) { ++ex->seq; }
 
 // waits for every rank's push of the current sequence number, then merges [world][2][nq_max][k_max] -> [nq][k]
 int exchange_wait_merge(frs_exchange* ex, int nq, int k, float* out_s, int64_t* out_i, cudaStream_t st) {
-  exchange_wait_kernel<<<1, 64, 0, st>>>(ex->flags, ex->world, ex->seq, ex->timeout_ns, ex->poison, ex->d_status);
-  EX_TRY(cudaGetLastError());
   const uint64_t* slot = ex->gather + (size_t)(ex->seq % kExchangeSlots) * ex->world * ex->block_words;
-  EX_TRY(launch_merge_shards(reinterpret_cast<const double*>(slot), reinterpret_cast<const int64_t*>(slot) + ex->plane_words,
-                             ex->world, nq, k, ex->block_words, out_s, out_i, st, ex->poison));
+  EX_TRY(launch_wait_merge_shards(ex->flags, ex->world, ex->seq, ex->timeout_ns, ex->poison, ex->d_status,
+                                  reinterpret_cast<const double*>(slot), reinterpret_cast<const int64_t*>(slot) + ex->plane_words,
+                                  nq, k, ex->block_words, out_s, out_i, st));
   return FRS_OK;
 }
 

@@ -773,7 +773,7 @@ extern "C" int frs_index_search_async(frs_index* idx, frs_exchange* ex, const fl
     idx->prof_calls++;
   }
   CU_TRY(cudaEventRecord(idx->job_done[slot], idx->s_merge));
-  idx->last_launches += ex ? 2 : 0;
+  idx->last_launches += ex ? 1 : 0;
   *ticket = slot;
   return FRS_OK;
 }
@@ -874,7 +874,7 @@ extern "C" int frs_index_search_host_submit(frs_index* idx, frs_exchange* ex, co
   if (e == cudaSuccess) e = cudaEventRecord(h.done, idx->s_merge);
   if (e == cudaSuccess) e = cudaEventRecord(idx->job_done[slot], idx->s_merge);
   if (e != cudaSuccess) return fail(set_err(FRS_E_CUDA, "cudaMemcpyAsync (results): %s", cudaGetErrorString(e)));
-  idx->last_launches += ex ? 2 : 0;
+  idx->last_launches += ex ? 1 : 0;
   *ticket = hsi;
   return FRS_OK;
 }

@@ -937,14 +937,13 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
 // ---------------------------------------------------------------------------------------------
 // cross-shard merge: [n_shards, nq, k] exact (fp64 score, global id) -> [nq, k]; one warp per query
 // ---------------------------------------------------------------------------------------------
-__global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_t* __restrict__ ids,
-                                    int n_shards, int nq, int k, size_t shard_stride,
-                                    float* __restrict__ out_s32, int64_t* __restrict__ out_ids,
-                                    const uint32_t* __restrict__ poison) {
+__device__ __forceinline__ void merge_shards_body(const double* __restrict__ s64, const int64_t* __restrict__ ids,
+                                                  int n_shards, int k, size_t shard_stride, float* __restrict__ out_s32,
+                                                  int64_t* __restrict__ out_ids, bool poisoned) {
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
   const int total = n_shards * k;
-  if (poison && __ldcg(poison) != 0u) {  // the exchange timed out: never hand out a partially gathered result
+  if (poisoned) {  // the exchange timed out: never hand out a partially gathered result
     for (int r = lane; r < k; r += 32) {
       out_s32[(size_t)q * k + r] = -INFINITY;
       out_ids[(size_t)q * k + r] = -1;
@@ -984,6 +983,45 @@ __global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_
     out_s32[(size_t)q * k + r] = -INFINITY;
     out_ids[(size_t)q * k + r] = -1;
   }
+}
+
+__global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_t* __restrict__ ids,
+                                    int n_shards, int nq, int k, size_t shard_stride,
+                                    float* __restrict__ out_s32, int64_t* __restrict__ out_ids,
+                                    const uint32_t* __restrict__ poison) {
+  merge_shards_body(s64, ids, n_shards, k, shard_stride, out_s32, out_ids, poison && __ldcg(poison) != 0u);
+}
+
+// The exchange's wait + cross-shard merge in ONE launch (csrc/exchange.cu): every CTA (one warp = one query) first
+// waits until all `world` ranks have published sequence number `seq` in this rank's flag words (lane r polls rank
+// r's flag, ld.acquire.sys), then merges.  The wait is bounded by wall-clock time; on time-out the exchange is poisoned
+// (sticky), the sequence number is reported to the host through `status` (pinned, host-mapped) and the query comes
+// back empty — nothing traps, the shard stays resident.
+__global__ void wait_merge_shards_kernel(const uint32_t* __restrict__ flags, int world, uint32_t seq,
+                                         unsigned long long timeout_ns, uint32_t* poison, uint32_t* status,
+                                         const double* __restrict__ s64, const int64_t* __restrict__ ids, int nq, int k,
+                                         size_t shard_stride, float* __restrict__ out_s32, int64_t* __restrict__ out_ids) {
+  bool bad = *reinterpret_cast<volatile uint32_t*>(poison) != 0u;
+  if (!bad) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (int r = threadIdx.x; r < world; r += 32) {
+      for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        __nanosleep(200);
+        if (globaltimer_ns() - t0 > timeout_ns || *reinterpret_cast<volatile uint32_t*>(poison) != 0u) {
+          *reinterpret_cast<volatile uint32_t*>(poison) = 1u;
+          *reinterpret_cast<volatile uint32_t*>(status) = seq;
+          __threadfence_system();
+          bad = true;
+          break;
+        }
+      }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+  }
+  merge_shards_body(s64, ids, world, k, shard_stride, out_s32, out_ids, bad);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1269,6 +1307,14 @@ cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_sha
   return cudaGetLastError();
 }
 
+cudaError_t launch_wait_merge_shards(const uint32_t* flags, int world, uint32_t seq, unsigned long long timeout_ns,
+                                     uint32_t* poison, uint32_t* status, const double* s64, const int64_t* ids, int nq, int k,
+                                     size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st) {
+  wait_merge_shards_kernel<<<nq, 32, 0, st>>>(flags, world, seq, timeout_ns, poison, status, s64, ids, nq, k, shard_stride,
+                                              out_s32, out_ids);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, const uint32_t* mask,
                                 int nq, void* qop, float* qrec, uint32_t* qcode, uint32_t* qmask,
                                 unsigned long long* stats, float* gmax, float* gsample, const void* rows,
@@ -1302,7 +1348,8 @@ cudaError_t preload_search_kernels() {
   const void* fns[] = {(const void*)scan_kernel<false, false>, (const void*)scan_kernel<true, false>,
                        (const void*)scan_kernel<false, true>,  (const void*)scan_kernel<true, true>,
                        (const void*)merge_kernel<false>,       (const void*)merge_kernel<true>,
-                       (const void*)merge_shards_kernel,       (const void*)prep_queries_kernel<false>,
+                       (const void*)merge_shards_kernel,       (const void*)wait_merge_shards_kernel,
+                       (const void*)prep_queries_kernel<false>,
                        (const void*)prep_queries_kernel<true>, (const void*)store_rows_kernel<false>,
                        (const void*)store_rows_kernel<true>,   (const void*)read_rows_kernel<false>,
                        (const void*)read_rows_kernel<true>};

@@ -122,6 +122,10 @@ cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st);
 cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
                                 size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st,
                                 const uint32_t* poison = nullptr);
+// the exchange's bounded wait for all ranks' sequence flags fused with the cross-shard merge (one launch per batch)
+cudaError_t launch_wait_merge_shards(const uint32_t* flags, int world, uint32_t seq, unsigned long long timeout_ns,
+                                     uint32_t* poison, uint32_t* status, const double* s64, const int64_t* ids, int nq, int k,
+                                     size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st);
 // queries [nq,384] fp32 -> qop (MMA operand, bf16 or tf32-rounded fp32, zero padded to 32 rows),
 // qrec (fp32 record copy), qcode/qmask copies padded to 32
 // also scores a strided sample of the stored rows against the prepared queries (bootstrap bound)
