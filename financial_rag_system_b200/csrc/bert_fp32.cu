@@ -77,11 +77,18 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const flo
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 8 x 8 outputs each
   const int lrow = tid >> 2, lk = (tid & 3) * 4;  // loader: rows lrow and lrow + 64, k offset lk..lk+3
+  // Two-level accumulation: fp32 FFMA over one 16-wide K tile, then the tile's partial sum is added in fp64.  The rounding
+  // error of a K = 1536 dot product then looks like that of a 16-term one (this is the PARITY mode: its job is to sit inside
+  // 1e-5 of an fp32 reference whose own summation order is different).
   float acc[8][8];
+  double dacc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      acc[i][j] = 0.f;
+      dacc[i][j] = 0.0;
+    }
   float4 ra[2], rw[2];
   auto gload = [&](int k0) {
 #pragma unroll
@@ -118,6 +125,13 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const flo
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dacc[i][j] += (double)acc[i][j];
+        acc[i][j] = 0.f;
+      }
     if (kt + 1 < nk) {
       sstore(buf ^ 1);
       __syncthreads();
@@ -130,7 +144,7 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const flo
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = n0 + tx * 8 + j;
-      float v = acc[i][j] + bias[c];
+      float v = (float)(dacc[i][j] + (double)bias[c]);
       if (EPI == kSGelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
       if (EPI == kSResidual) v += resid[(size_t)r * N + c];
       C[(size_t)r * N + c] = v;

@@ -19,7 +19,8 @@ Tolerances (north_star: "1e-2 absolute for bf16"):
                                                           what rerank_documents uses — is asserted to be the oracle's.
     per-stage activations of one layer                    <= 0.05 absolute on O(1) values
 fp32 mode (precision="fp32": fp32 weights, activations and FFMA arithmetic, no tensor cores), north_star "1e-5":
-    embedding components <= 1e-5, last hidden state <= 1e-4 on O(5) values, reranker logits <= 1e-4
+    embedding components <= 1e-5, reranker logits <= 1e-5, last hidden state <= 2e-5 on O(5) values (the GEMMs add
+    each 16-wide K tile's fp32 partial sum in fp64: measured 3e-7 / 7e-6 / 6e-6)
 """
 import numpy as np
 import pytest
@@ -317,14 +318,14 @@ def test_fp32_mode_meets_the_1e5_bound():
     hid = enc.last_hidden(int(cu[-1])).cpu().numpy()
     ref_h = eo.last_hidden_packed(BGE_SMALL, w, ids, cu)
     print(f"fp32 last hidden: max err {np.abs(hid - ref_h).max():.2e}")
-    assert np.abs(hid - ref_h).max() <= 1e-4
+    assert np.abs(hid - ref_h).max() <= 2e-5   # O(5) values
     enc.close()
     wc = synthetic_checkpoint(MINILM_L6_CE, 4321)
     ce32 = BertEncoder(MINILM_L6_CE, wc, device=0, max_tokens=2048, precision="fp32")
     got = ce32.score_packed(ids, tts, cu)
     ref = eo.score_pairs(MINILM_L6_CE, wc, ids, tts, cu)
     print(f"fp32 logits: max err {np.abs(got - ref).max():.2e}")
-    assert np.abs(got - ref).max() <= 1e-4
+    assert np.abs(got - ref).max() <= 1e-5   # north_star's bound for the fp32 mode (measured 7e-6)
     ce32.close()
 
 
