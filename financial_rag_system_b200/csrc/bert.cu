@@ -339,7 +339,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int tile_step = (int)num_clusters_x();
   // (row tile, column tile) of this CTA for a cluster tile.  A phantom row tile (odd num_mtiles) loads zeros and
   // its stores are clipped by the tensor map.
-  auto tile_mt = [&](int tile) { return 2 * (tile / nt_count) + (int)crank; };
+  auto tile_mt = [&](int tile) { return p.mtile0 + 2 * (tile / nt_count) + (int)crank; };
   auto tile_nt = [&](int tile) { return tile % nt_count; };
 
   if (threadIdx.x == 0) {

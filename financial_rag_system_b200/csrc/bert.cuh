@@ -32,7 +32,8 @@ enum GemmEpi {
 
 struct GemmParams {
   int M;           // live token rows
-  int num_mtiles;  // ceil(M / 128)
+  int num_mtiles;  // row tiles this launch covers (ceil(M / 128) for the whole batch)
+  int mtile0;      // first row tile of this launch (even): a launch may cover a slice of the rows (FFN row chunks)
   int N, K;
   const float* bias;   // [N]
   float qscale;
