@@ -388,6 +388,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after();
   cluster_sync_all();  // the peer's mbarriers exist before anybody arrives on them
   const uint32_t tmem_base = *holder;
+  // everything above touched only this kernel's own shared / tensor memory and the (constant) weights: it may overlap the
+  // previous kernel's tail.  Activations are read, and buffers overwritten, only after the previous grid has completed.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -892,6 +896,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder + grp * kTmemCols;
+  pdl_launch_dependents();
+  pdl_wait();  // (see gemm_kernel: the prologue above overlaps the previous kernel's tail)
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAttnRegsLow));
   if (warp == 0) {
@@ -1346,6 +1352,12 @@ cudaError_t launch_embed_ln(const int32_t* ids, const int32_t* type_ids, const i
   return cudaGetLastError();
 }
 
+// FRS_NO_PDL=1 launches every kernel fully serialised (A/B measurements)
+static bool pdl_enabled() {
+  static const bool on = getenv("FRS_NO_PDL") == nullptr;
+  return on;
+}
+
 template <int BN, int EPI>
 static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                                  const CUtensorMap& to2, const GemmParams& p, cudaStream_t st) {
@@ -1397,13 +1409,15 @@ static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUte
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue overlaps the previous kernel's tail (pdl_wait)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI>, ta, tb, to, to2, pd);
 }
 
@@ -1419,6 +1433,21 @@ cudaError_t launch_gemm(int epi, int sm_count, const CUtensorMap& tmap_a, const 
 }
 
 int attn_key_block() { return kKB; }
+
+static cudaError_t launch_attention_kernel(int grid, size_t smem, cudaStream_t st, const CUtensorMap& tmap_qk,
+                                           const CUtensorMap& tmap_k, const CUtensorMap& tmap_vt, const AttnParams& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attention_kernel, tmap_qk, tmap_k, tmap_vt, p);
+}
 
 cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_k, const CUtensorMap& tmap_vt,
                              const AttnParams& p, cudaStream_t st) {
@@ -1489,8 +1518,7 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
   }
   return cudaGetLastError();
 #endif
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>(tmap_qk, tmap_k, tmap_vt, p);
-  return cudaGetLastError();
+  return launch_attention_kernel(grid, smem, st, tmap_qk, tmap_k, tmap_vt, p);
 }
 
 cudaError_t launch_pool_normalize(const __nv_bfloat16* x, const int32_t* cu_seqlens, const int32_t* row_start,

@@ -21,6 +21,14 @@ __device__ __forceinline__ uint32_t lane_id() {
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
   return l;
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident (and run its prologue: barrier init, TMEM allocation, descriptor prefetch, weight staging) while the previous
+// kernel of the stream is still draining.  pdl_wait() blocks until that previous grid has COMPLETED and its memory is
+// visible; everything that reads the previous kernel's output or overwrites its inputs comes after it.
+// pdl_launch_dependents() lets the next kernel of the stream start becoming resident as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
