@@ -23,7 +23,9 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-CHUNKS_PER_STEP = 128     # x 512 tokens = 65536 packed tokens per pass and per GPU
+CHUNKS_PER_STEP = 148     # x 512 tokens = 75776 packed tokens per pass and per GPU: one chunk per SM, so every kernel's tile
+                          # count is a multiple of its grid (592 row tiles = 4 x 148; 128 chunks left the LayerNorm GEMMs'
+                          # fourth round of 256-row pair tiles 46 % empty)
 SEQ = 512
 NQ, LIMIT, TOP_K = 32, 15, 5
 PIPE_ROWS = int(os.environ.get("FRS_PIPE_ROWS", 100_000))
@@ -55,9 +57,9 @@ def unit_name(workload):
 def config(workload, world):
     if workload == "embed":
         return {"workload": f"bge-small-en-v1.5 shape (12 layers, 33.4M params, seeded synthetic weights), {CHUNKS_PER_STEP} chunks x {SEQ} "
-                            f"tokens per step and per GPU, CLS pooling + L2 normalise", "chunks_per_step_per_gpu": CHUNKS_PER_STEP,
+                            f"tokens per step and per GPU (one per SM), CLS pooling + L2 normalise", "chunks_per_step_per_gpu": CHUNKS_PER_STEP,
                 "seq_len": SEQ, "parallelism": f"{world} GPU(s), independent chunks, weights replicated, no collective",
-                "l2": "activations of one pass (~500 MB) exceed the 126 MB L2"}
+                "l2": "activations of one pass (~580 MB) exceed the 126 MB L2"}
     if workload == "rerank":
         return {"workload": f"ms-marco-MiniLM-L-6-v2 shape (6 layers, 22.7M params, seeded synthetic weights), {NQ}x{LIMIT} = {NQ * LIMIT} "
                             "(query, ~1000-char chunk) pairs per step, raw logits", "pairs_per_step_per_gpu": NQ * LIMIT,
