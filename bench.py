@@ -459,6 +459,10 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
         step()
     drain()
     cx.barrier()
+    if os.environ.get("FRS_BENCH_TIMELINE") and cx.rank == 0:
+        tl = ix.read_profile_raw(min(steps, 200))
+        np.savetxt(os.path.join(ROOT, "gpurun_out", f"timeline_n{cx.world}.txt"), tl, fmt="%.4f",
+                   header="prep_start prep_end scan_start scan_end merge_start merge_end exchange_end (ms)")
     prof = ix.read_profile_ex()
     ix.set_profiling(0)
     n = max(prof["n"], 1)

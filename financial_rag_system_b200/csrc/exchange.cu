@@ -71,6 +71,8 @@ void free_exchange(frs_exchange* ex) {
   cudaFree(ex->local);
   cudaFree(ex->counter);
   cudaFree(ex->poison);
+  for (void* ev : ex->merged)
+    if (ev) cudaEventDestroy((cudaEvent_t)ev);
   if (ex->h_status) cudaFreeHost(const_cast<uint32_t*>(ex->h_status));
   delete ex;
 }
@@ -116,6 +118,12 @@ extern "C" int frs_exchange_create(int device, int world, int rank, int nq_max, 
   if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->block_words * 8);
   if (e == cudaSuccess) e = cudaMemset(ex->counter, 0, 4);
   if (e == cudaSuccess) e = cudaMemset(ex->poison, 0, 4);
+  static_assert(kExchangeSlots == 4, "frs_exchange::merged has one event per gather slot");
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+    cudaEvent_t ev = nullptr;
+    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    ex->merged[i] = ev;
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     free_exchange(ex);
@@ -285,5 +293,9 @@ extern "C" int frs_exchange_wait_merge_n(frs_exchange* ex, int nq, int k, float*
   if (!ex->connected || ex->seq == 0) return abi_set_err(FRS_E_INVALID, "nothing was pushed");
   if (nq < 1 || nq > ex->nq_max || k < 1 || k > ex->k_max) return abi_set_err(FRS_E_INVALID, "nq / k exceed the exchange's");
   EX_TRY(cudaSetDevice(ex->device));
-  return frs::exchange_wait_merge(ex, nq, k, dev_out_scores, dev_out_ids, (cudaStream_t)stream);
+  int rc = frs::exchange_wait_merge(ex, nq, k, dev_out_scores, dev_out_ids, (cudaStream_t)stream);
+  if (rc) return rc;
+  // (the pipelined forms order the push of sequence number s + 2 behind this merge of s: gather slots are a ring)
+  EX_TRY(cudaEventRecord((cudaEvent_t)ex->merged[ex->seq % kExchangeSlots], (cudaStream_t)stream));
+  return FRS_OK;
 }

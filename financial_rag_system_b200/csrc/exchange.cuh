@@ -21,6 +21,9 @@ struct frs_exchange {
   volatile uint32_t* h_status = nullptr;
   uint32_t* d_status = nullptr;
   unsigned long long timeout_ns = 30ull * 1000 * 1000 * 1000;
+  // merged[s % kSlots]: recorded (on the stream that ran it) after this rank's cross-shard merge of sequence number s.
+  // The push of s + 2 waits for it: gather slots are a ring of four (see scan.cuh: D >= 2 d).
+  void* merged[4] = {nullptr, nullptr, nullptr, nullptr};  // cudaEvent_t
   std::vector<void*> opened;          // IPC mappings to close
   uint32_t seq = 0;
   bool connected = false;

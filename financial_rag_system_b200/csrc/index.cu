@@ -157,9 +157,11 @@ static void free_index(frs_index* ix) {
     if (ix->job_prep[i]) cudaEventDestroy(ix->job_prep[i]);
     if (ix->job_scan[i]) cudaEventDestroy(ix->job_scan[i]);
     if (ix->job_done[i]) cudaEventDestroy(ix->job_done[i]);
+    if (ix->job_merge[i]) cudaEventDestroy(ix->job_merge[i]);
   }
   if (ix->rows_ready) cudaEventDestroy(ix->rows_ready);
-  for (cudaStream_t s : {ix->s_prep, ix->s_scan[0], ix->s_scan[1], ix->s_merge, ix->stream})
+  if (ix->xchg_last) cudaEventDestroy(ix->xchg_last);
+  for (cudaStream_t s : {ix->s_prep, ix->s_scan[0], ix->s_scan[1], ix->s_merge, ix->s_xchg, ix->stream})
     if (s) cudaStreamDestroy(s);
   delete ix;
 }
@@ -180,7 +182,7 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
                    prop.major, prop.minor);
   frs_index* ix = new (std::nothrow) frs_index();
   if (!ix) return set_err(FRS_E_INVALID, "out of host memory");
-  for (int i = 0; i < kJobRing; ++i) ix->job_in[i] = ix->job_prep[i] = ix->job_scan[i] = ix->job_done[i] = nullptr;
+  for (int i = 0; i < kJobRing; ++i) ix->job_in[i] = ix->job_prep[i] = ix->job_scan[i] = ix->job_done[i] = ix->job_merge[i] = nullptr;
   ix->device = device;
   ix->dtype = dtype;
   ix->capacity = capacity;
@@ -233,6 +235,7 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
     IX_TRY(cudaEventCreateWithFlags(&ix->job_prep[i], cudaEventDisableTiming));
     IX_TRY(cudaEventCreateWithFlags(&ix->job_scan[i], cudaEventDisableTiming));
     IX_TRY(cudaEventCreateWithFlags(&ix->job_done[i], cudaEventDisableTiming));
+    IX_TRY(cudaEventCreateWithFlags(&ix->job_merge[i], cudaEventDisableTiming));
   }
   IX_TRY(cudaEventCreateWithFlags(&ix->rows_ready, cudaEventDisableTiming));
   // prep / merge / exchange kernels are short and gate the next scan: when an SM frees up they go first
@@ -242,6 +245,8 @@ extern "C" int frs_index_create(int device, int dim, int64_t capacity, int dtype
   IX_TRY(cudaStreamCreateWithPriority(&ix->s_scan[0], cudaStreamNonBlocking, prio_lo));
   IX_TRY(cudaStreamCreateWithPriority(&ix->s_scan[1], cudaStreamNonBlocking, prio_lo));
   IX_TRY(cudaStreamCreateWithPriority(&ix->s_merge, cudaStreamNonBlocking, prio_hi));
+  IX_TRY(cudaStreamCreateWithPriority(&ix->s_xchg, cudaStreamNonBlocking, prio_hi));
+  IX_TRY(cudaEventCreateWithFlags(&ix->xchg_last, cudaEventDisableTiming));
   IX_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   IX_TRY(preload_search_kernels());
   IX_TRY(cudaDeviceSynchronize());  // the memsets above ran on the legacy stream; the internal streams do not sync with it
@@ -651,6 +656,25 @@ int exchange_check(frs_exchange* ex);
 
 }  // namespace frs
 
+// Ring-slot rule of the gather buffers (scan.cuh): the push of sequence number s may be issued only after this rank's own
+// cross-shard merge of s - 2.  Called before the local pass whose merge kernel carries the push of ex->seq + 1.
+static int exchange_order_push(frs_index* ix, frs_exchange* ex) {
+  const uint32_t next = ex->seq + 1;
+  if (next > 2) CU_TRY(cudaStreamWaitEvent(ix->s_merge, (cudaEvent_t)ex->merged[(next - 2) % kExchangeSlots], 0));
+  return FRS_OK;
+}
+
+// The cross-shard half of a pipelined sharded search, on its own stream: wait for every rank's push of ex->seq (already
+// committed), merge into the caller's outputs.  Leaves s_xchg ordered behind the local merge of this job.
+static int exchange_tail(frs_index* ix, frs_exchange* ex, int job, int nq, int k, float* out_s, int64_t* out_i) {
+  CU_TRY(cudaEventRecord(ix->job_merge[job], ix->s_merge));
+  CU_TRY(cudaStreamWaitEvent(ix->s_xchg, ix->job_merge[job], 0));
+  int rc = exchange_wait_merge(ex, nq, k, out_s, out_i, ix->s_xchg);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord((cudaEvent_t)ex->merged[ex->seq % kExchangeSlots], ix->s_xchg));
+  return FRS_OK;
+}
+
 static SearchLaunch in_stream_launch(frs_index* ix, cudaStream_t st) {
   SearchLaunch L{};
   L.prep = L.scan = L.merge = st;
@@ -761,18 +785,25 @@ extern "C" int frs_index_search_async(frs_index* idx, frs_exchange* ex, const fl
   int slot = 0;
   rc = pipelined_begin(idx, true, (cudaStream_t)in_stream, &slot, &L);
   if (rc) return rc;
+  if (ex && (rc = exchange_order_push(idx, ex))) return rc;
   rc = search_enqueue(idx, a, L);
   if (rc) return rc;
+  cudaStream_t tail = idx->s_merge;  // the stream the job's last operation runs on
   if (ex) {
     exchange_commit_push(ex);
-    rc = exchange_wait_merge(ex, nq, k, dev_out_scores, dev_out_ids, idx->s_merge);
+    rc = exchange_tail(idx, ex, slot, nq, k, dev_out_scores, dev_out_ids);
     if (rc) return rc;
+    tail = idx->s_xchg;
   }
   if (L.prof) {
-    CU_TRY(cudaEventRecord(L.prof[6], idx->s_merge));
+    CU_TRY(cudaEventRecord(L.prof[6], tail));
     idx->prof_calls++;
   }
-  CU_TRY(cudaEventRecord(idx->job_done[slot], idx->s_merge));
+  CU_TRY(cudaEventRecord(idx->job_done[slot], tail));
+  if (ex) {
+    CU_TRY(cudaEventRecord(idx->xchg_last, tail));
+    idx->xchg_used = true;
+  }
   idx->last_launches += ex ? 1 : 0;
   *ticket = slot;
   return FRS_OK;
@@ -784,7 +815,8 @@ extern "C" int frs_index_wait(frs_index* idx, int ticket, void* stream) {
   std::lock_guard<std::mutex> lk(idx->mu);
   if (ticket < 0) {
     if (idx->jobs == 0) return FRS_OK;
-    ticket = (int)((idx->jobs - 1) % kJobRing);  // the merge stream is in order: the newest job finishes last
+    ticket = (int)((idx->jobs - 1) % kJobRing);  // each tail stream is in order: its newest job finishes last
+    if (idx->xchg_used) CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, idx->xchg_last, 0));
   }
   CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, idx->job_done[ticket], 0));
   return FRS_OK;
@@ -793,16 +825,18 @@ extern "C" int frs_index_wait(frs_index* idx, int ticket, void* stream) {
 extern "C" int frs_index_sync(frs_index* idx, int ticket) {
   if (!idx || ticket >= kJobRing) return set_err(FRS_E_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(idx->device));
-  cudaEvent_t ev;
+  cudaEvent_t ev, ev2 = nullptr;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     if (ticket < 0) {
       if (idx->jobs == 0) return FRS_OK;
       ticket = (int)((idx->jobs - 1) % kJobRing);
+      if (idx->xchg_used) ev2 = idx->xchg_last;
     }
     ev = idx->job_done[ticket];
   }
   CU_TRY(cudaEventSynchronize(ev));
+  if (ev2) CU_TRY(cudaEventSynchronize(ev2));
   return FRS_OK;
 }
 
@@ -859,20 +893,27 @@ extern "C" int frs_index_search_host_submit(frs_index* idx, frs_exchange* ex, co
   if (rc) return fail(rc);
   cudaError_t e = cudaMemcpyAsync(h.d_in, h.h_in, qb + (size_t)nq * 8, cudaMemcpyHostToDevice, idx->s_prep);
   if (e != cudaSuccess) return fail(set_err(FRS_E_CUDA, "cudaMemcpyAsync (queries): %s", cudaGetErrorString(e)));
+  if (ex && (rc = exchange_order_push(idx, ex))) return fail(rc);
   rc = search_enqueue(idx, a, L);
   if (rc) return fail(rc);
+  cudaStream_t tail = idx->s_merge;
   if (ex) {
     exchange_commit_push(ex);
-    rc = exchange_wait_merge(ex, nq, k, d_scores, d_ids, idx->s_merge);
+    rc = exchange_tail(idx, ex, slot, nq, k, d_scores, d_ids);
     if (rc) return fail(rc);
+    tail = idx->s_xchg;
   }
   if (L.prof) {
-    cudaEventRecord(L.prof[6], idx->s_merge);
+    cudaEventRecord(L.prof[6], tail);
     idx->prof_calls++;
   }
-  e = cudaMemcpyAsync(h.h_out, h.d_out, (size_t)nq * k * 12, cudaMemcpyDeviceToHost, idx->s_merge);
-  if (e == cudaSuccess) e = cudaEventRecord(h.done, idx->s_merge);
-  if (e == cudaSuccess) e = cudaEventRecord(idx->job_done[slot], idx->s_merge);
+  e = cudaMemcpyAsync(h.h_out, h.d_out, (size_t)nq * k * 12, cudaMemcpyDeviceToHost, tail);
+  if (e == cudaSuccess) e = cudaEventRecord(h.done, tail);
+  if (e == cudaSuccess) e = cudaEventRecord(idx->job_done[slot], tail);
+  if (e == cudaSuccess && ex) {
+    e = cudaEventRecord(idx->xchg_last, tail);
+    idx->xchg_used = true;
+  }
   if (e != cudaSuccess) return fail(set_err(FRS_E_CUDA, "cudaMemcpyAsync (results): %s", cudaGetErrorString(e)));
   idx->last_launches += ex ? 1 : 0;
   *ticket = hsi;
@@ -1071,6 +1112,26 @@ extern "C" int frs_index_read_profile_ex(frs_index* idx, double* host_out8) {
   host_out8[0] = n;
   idx->prof_calls = 0;
   return FRS_OK;
+}
+
+// Raw time line of the recorded searches (oldest first): per search 7 event times in ms relative to the first search's
+// first event — {prep start, prep end, scan start, scan end, merge start, merge end, exchange end}.  Returns the count.
+extern "C" int frs_index_read_profile_raw(frs_index* idx, double* host_out, int max_searches) {
+  if (!idx || !host_out || max_searches < 1) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (!idx->prof_ev || idx->prof_calls == 0 || idx->prof_mode == 3) return 0;
+  int n = idx->prof_calls < frs_index::kProfRing ? idx->prof_calls : frs_index::kProfRing;
+  if (n > max_searches) n = max_searches;
+  auto evs = [&](int c) { return idx->prof_ev + (size_t)((idx->prof_calls - n + c) % frs_index::kProfRing) * kProfEvents; };
+  CU_TRY(cudaEventSynchronize(evs(n - 1)[6]));
+  for (int c = 0; c < n; ++c)
+    for (int j = 0; j < 7; ++j) {
+      float ms = 0.f;
+      CU_TRY(cudaEventElapsedTime(&ms, evs(0)[0], evs(c)[j]));
+      host_out[c * 7 + j] = ms;
+    }
+  return n;
 }
 
 extern "C" int frs_index_read_profile(frs_index* idx, double* host_out4) {

@@ -98,10 +98,16 @@ struct frs_index {
   // Consecutive scans alternate between TWO streams: they are independent kernels (separate workspaces), so the
   // CTAs of scan i+1 start on SMs as the CTAs of scan i leave them — the ramp of one launch fills the tail of the
   // previous one instead of both being bubbles (at 1.25M rows per GPU they were ~15 % of a launch).
-  cudaStream_t s_prep = nullptr, s_scan[2] = {nullptr, nullptr}, s_merge = nullptr;
+  // s_xchg: the cross-shard wait + merge of a sharded search.  Not on s_merge: the wait for the slowest peer's push of
+  // batch i would hold up this rank's LOCAL merge of batch i+1 behind it, the workspace ring would fill and the scans
+  // stall (8 GPUs, 1.25M rows each: the in-order chain merge -> wait -> merge took 100-300 us per batch, the scan 150).
+  cudaStream_t s_prep = nullptr, s_scan[2] = {nullptr, nullptr}, s_merge = nullptr, s_xchg = nullptr;
   int scan_streams = 2;
   cudaStream_t stream = nullptr;  // host-call write path (add_host, read_rows_host)
   cudaEvent_t job_in[frs::kJobRing], job_prep[frs::kJobRing], job_scan[frs::kJobRing], job_done[frs::kJobRing];
+  cudaEvent_t job_merge[frs::kJobRing];  // local merge (+ push) enqueued: hand-over s_merge -> s_xchg
+  cudaEvent_t xchg_last = nullptr;       // recorded on s_xchg after the newest sharded job
+  bool xchg_used = false;
   uint64_t jobs = 0;
   cudaEvent_t rows_ready = nullptr;  // recorded after the last write-path kernel; every search waits on it
   bool writes_pending = false;       // a write was issued and rows_ready has not been seen complete yet

@@ -322,6 +322,15 @@ class VectorIndex:
         d["n"] = int(d["n"])
         return d
 
+    def read_profile_raw(self, max_searches: int = 256) -> np.ndarray:
+        """[n, 7] ms: prep start / end, scan start / end, merge start / end, exchange end of the recorded searches
+        (oldest first), relative to the first one's prep start.  Call before read_profile[_ex] (which resets)."""
+        buf = (C.c_double * (7 * max_searches))()
+        n = self._lib.frs_index_read_profile_raw(self._h, buf, int(max_searches))
+        if n < 0:
+            check(n)
+        return np.array(buf[:7 * n], dtype=np.float64).reshape(n, 7)
+
     def read_timeline(self, n_ctas: int) -> np.ndarray:
         out = np.zeros((n_ctas, 16), dtype=np.uint64)
         check(self._lib.frs_index_read_timeline(self._h, _ptr(out), n_ctas))

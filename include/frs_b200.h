@@ -282,6 +282,10 @@ int frs_index_read_profile(frs_index* idx, double* host_out4);
 /* {searches, prep ms, scan ms, merge ms, exchange ms (cross-shard wait + merge), scan-stream gap ms (end of one
  * scan kernel to the start of the next, summed), span ms (first prep start to last search end), 0} */
 int frs_index_read_profile_ex(frs_index* idx, double* host_out8);
+/* raw time line (diagnostics): per recorded search, oldest first, 7 event times in ms relative to the first search's first
+ * event {prep start, prep end, scan start, scan end, merge start, merge end, exchange end}; returns the number of searches
+ * written (<= max_searches), does not reset the recording */
+int frs_index_read_profile_raw(frs_index* idx, double* host_out, int max_searches);
 /* [n_ctas, 16] globaltimer ns: start, first slab landed, last MMA issued, first tile consumed,
  * last tile consumed, exit, then stamps of the first rare-path invocation (diagnostics) */
 int frs_index_read_timeline(frs_index* idx, uint64_t* host_out, int n_ctas);
