@@ -8,7 +8,10 @@
 //          sequence number in the peer's flag word.  frs_index_search_push (index.cu) does this in the TAIL OF
 //          THE LOCAL MERGE KERNEL (scan.cu merge_kernel: one CTA per query pushes its k results, the last CTA
 //          publishes the flags); frs_exchange_push is the stand-alone form for a block that already exists;
-//   wait   a one-warp kernel spins until all `world` flags have reached the current sequence number.  The wait is
+//   wait   the HEAD of the cross-shard merge kernel (scan.cu wait_merge_shards_kernel): one warp polls the `world`
+//          flags (ld.acquire.sys) until all have reached the current sequence number, then the block merges.  In the
+//          pipelined engine that kernel runs on the index's own exchange stream (index.cu exchange_tail), so a late
+//          peer holds up nothing but this batch's final result.  The wait is
 //          bounded by a wall-clock time-out (default 30 s, frs_exchange_set_timeout_ms): a rank that is merely late
 //          (host stall, lazy module load, a save in progress) is waited for; a lost one poisons the batch — the
 //          merge emits an empty result and the host entry points return FRS_E_TIMEOUT — instead of trapping,
@@ -19,8 +22,8 @@
 // resident next to the persistent scan kernel, and the latency is one store + one flag per peer.
 //
 // Buffer reuse: gather buffers are a ring of kExchangeSlots = 4 batches (scan.cuh): a rank may issue the push of
-// batch t + 2 only after its own final merge of batch t (ShardedIndex.search_async orders its streams that way; the
-// synchronous form pushes t + 1 after merging t), which keeps a slot from being overwritten while a peer still
+// batch t + 2 only after its own final merge of batch t (index.cu exchange_order_push makes the merge stream wait for
+// the event `merged[(t) % 4]`; the synchronous form pushes t + 1 after merging t), which keeps a slot from being overwritten while a peer still
 // reads it.  Flags are monotonic (no reset, no ABA).
 //
 // The reference has no counterpart (one Qdrant server, main.py:215-239); this is north-star item (3), the exchange
