@@ -449,6 +449,10 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     ms_own = e0.elapsed_time(e1)
     ms = cx.max_over_ranks(ms_own)
     ids, scores = (last.ids, last.scores) if tiles_dev is None else last
+    fill_drain = None
+    if tiles_dev is None:
+        torch.cuda.synchronize()
+        fill_drain = ix.read_profile_bracket_rel(e0, e1)
     bracket = ix.read_profile_ex() if tiles_dev is None else None
 
     # ---- region B: per-kernel events of the same pipelined steps (seven events per step: the breakdown; the events
@@ -480,6 +484,12 @@ def measure_search(cx, ix, sh, hq, dq, steps, warmup, length, row_bytes, tiles_d
     else:
         out["scan_ms_source"] = "per-launch CUDA events of a separate profiling pass"
     out["scan_ms"] = scan_ms
+    if fill_drain is not None:
+        # per rank: the scan kernels' average duration in region A, and the parts of the region before the first scan
+        # kernel (prep of batch 0) and after the last one (merge + exchange of the last batches, peers that lag)
+        out["per_rank"] = {"scan_ms": [round(v, 5) for v in cx.gather_floats(scan_ms)],
+                           "fill_ms": [round(v, 4) for v in cx.gather_floats(fill_drain[0])],
+                           "drain_ms": [round(v, 4) for v in cx.gather_floats(fill_drain[1])]}
     alg_bytes = (int(tiles_dev.numel()) * 128 if tiles_dev is not None else length) * (row_bytes + 4)
     out["alg_bytes"] = alg_bytes
     out["achieved"] = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
@@ -727,6 +737,7 @@ def run_ours(args):
             "breakdown_ms": {k: round(v, 5) for k, v in r["breakdown"].items()},
             "host_enqueue_us_per_step": round(r["host_enqueue_us_per_step"], 1),
             "timed_region_ms_per_rank": [round(v, 4) for v in r["ms_per_rank"]],
+            "per_rank": r.get("per_rank"),
             "scan_stats_last_step": {k: r["stats"][k] for k in ("appended", "compactions", "resolutions", "rescored", "grid")},
             "parity_checked": checked, "prefilter_max_err": pre_err, "prefilter_eps": 3e-5,
             "comm": ("peer-memory stores + flags inside the merge kernel (csrc/exchange.cu); NCCL is used for process-group set-up and "

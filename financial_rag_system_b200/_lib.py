@@ -98,6 +98,7 @@ PROTOTYPES = {
     "frs_index_set_profiling": (_int, [_vp, _int]),
     "frs_index_read_profile": (_int, [_vp, C.POINTER(C.c_double)]),
     "frs_index_read_profile_ex": (_int, [_vp, C.POINTER(C.c_double)]),
+    "frs_index_read_profile_bracket_rel": (_int, [_vp, _vp, _vp, C.POINTER(C.c_double)]),
     "frs_index_read_profile_raw": (_int, [_vp, C.POINTER(C.c_double), _int]),
     "frs_index_read_timeline": (_int, [_vp, _vp, _int]),
     "frs_encoder_create": (_int, [_int, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),

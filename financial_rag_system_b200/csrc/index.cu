@@ -1065,6 +1065,25 @@ extern "C" int frs_index_set_profiling(frs_index* idx, int mode) {
   return FRS_OK;
 }
 
+// Bracket profiling (mode 3) relative to the caller's own events: out2 = {ms from `ev_before` to the start of the first scan
+// kernel, ms from the end of the last scan kernel to `ev_after`} — the fill and the drain of a pipelined run.  Both events
+// must have been recorded on this device (cudaEvent_t handles, e.g. torch.cuda.Event.cuda_event) and completed.
+extern "C" int frs_index_read_profile_bracket_rel(frs_index* idx, void* ev_before, void* ev_after, double* host_out2) {
+  if (!idx || !ev_before || !ev_after || !host_out2) return set_err(FRS_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  host_out2[0] = host_out2[1] = 0.0;
+  if (idx->prof_mode != 3 || !idx->br_first || idx->br_count == 0) return set_err(FRS_E_INVALID, "no bracket recorded (set_profiling(3), then search)");
+  CU_TRY(cudaEventSynchronize(idx->br_last));
+  CU_TRY(cudaEventSynchronize((cudaEvent_t)ev_after));
+  float a = 0.f, b = 0.f;
+  CU_TRY(cudaEventElapsedTime(&a, (cudaEvent_t)ev_before, idx->br_first));
+  CU_TRY(cudaEventElapsedTime(&b, idx->br_last, (cudaEvent_t)ev_after));
+  host_out2[0] = a;
+  host_out2[1] = b;
+  return FRS_OK;
+}
+
 // out8: {searches, prep ms, scan ms, merge ms, exchange ms (cross-shard wait + merge; 0 for a plain search),
 //        scan-stream gap ms (end of one scan kernel -> start of the next, summed over consecutive searches),
 //        span ms (first prep start -> last search end), 0}

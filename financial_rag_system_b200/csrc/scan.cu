@@ -935,36 +935,77 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
 }
 
 // ---------------------------------------------------------------------------------------------
-// cross-shard merge: [n_shards, nq, k] exact (fp64 score, global id) -> [nq, k]; one warp per query
+// cross-shard merge: [n_shards, nq, k] exact (fp64 score, global id) -> [nq, k]; one CTA of kShardMergeThreads per
+// query.  The n_shards * k candidates of the query are staged in shared memory with ONE round of independent L2 loads
+// (ld.global.cg: the words were written by peers over NVLink and sit in this GPU's L2 / HBM), then every thread ranks
+// its candidates against the staged list (rank = number of strictly better candidates; ties break by global id).  The
+// first version ranked straight from global memory, one warp per query: 4 x 120 dependent-latency loads per lane made
+// the kernel take ~70 us at 8 shards — and it sits on the critical chain of the pipelined exchange.
 // ---------------------------------------------------------------------------------------------
+constexpr int kShardMergeThreads = 128;
+constexpr int kShardMergeStage = 1024;  // candidates staged in shared memory (16 KB); more shards fall back to global reads
+
 __device__ __forceinline__ void merge_shards_body(const double* __restrict__ s64, const int64_t* __restrict__ ids,
                                                   int n_shards, int k, size_t shard_stride, float* __restrict__ out_s32,
                                                   int64_t* __restrict__ out_ids, bool poisoned) {
+  __shared__ double sh_s[kShardMergeStage];
+  __shared__ int64_t sh_id[kShardMergeStage];
+  __shared__ int sh_valid;
   const int q = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
   const int total = n_shards * k;
   if (poisoned) {  // the exchange timed out: never hand out a partially gathered result
-    for (int r = lane; r < k; r += 32) {
+    for (int r = tid; r < k; r += kShardMergeThreads) {
       out_s32[(size_t)q * k + r] = -INFINITY;
       out_ids[(size_t)q * k + r] = -1;
     }
     return;
   }
-  // each lane owns candidates lane, lane+32, ... ; rank = number of strictly better candidates
-  for (int c = lane; c < total; c += 32) {
+  const bool staged = total <= kShardMergeStage;
+  if (tid == 0) sh_valid = 0;
+  __syncthreads();
+  int valid = 0;
+  for (int c = tid; c < total; c += kShardMergeThreads) {
     const int sh = c / k, j = c - sh * k;
     const size_t off = (size_t)sh * shard_stride + (size_t)q * k + j;
-    const int64_t id = ids[off];
+    const int64_t id = __ldcg(ids + off);
+    valid += id >= 0;
+    if (staged) {
+      sh_id[c] = id;
+      sh_s[c] = __ldcg(s64 + off);
+    }
+  }
+  if (valid) atomicAdd(&sh_valid, valid);
+  __syncthreads();
+  for (int c = tid; c < total; c += kShardMergeThreads) {
+    int64_t id;
+    double s;
+    if (staged) {
+      id = sh_id[c];
+      s = sh_s[c];
+    } else {
+      const int sh = c / k, j = c - sh * k;
+      const size_t off = (size_t)sh * shard_stride + (size_t)q * k + j;
+      id = __ldcg(ids + off);
+      s = __ldcg(s64 + off);
+    }
     if (id < 0) continue;
-    const double s = s64[off];
     int rank = 0;
-    for (int d = 0; d < total; ++d) {
-      const int sh2 = d / k, j2 = d - sh2 * k;
-      const size_t off2 = (size_t)sh2 * shard_stride + (size_t)q * k + j2;
-      const int64_t id2 = ids[off2];
-      if (id2 < 0) continue;
-      const double s2 = s64[off2];
-      rank += (s2 > s) || (s2 == s && id2 < id);
+    if (staged) {
+      for (int d = 0; d < total; ++d) {
+        const int64_t id2 = sh_id[d];
+        const double s2 = sh_s[d];
+        rank += (id2 >= 0) && ((s2 > s) || (s2 == s && id2 < id));
+      }
+    } else {
+      for (int d = 0; d < total; ++d) {
+        const int sh2 = d / k, j2 = d - sh2 * k;
+        const size_t off2 = (size_t)sh2 * shard_stride + (size_t)q * k + j2;
+        const int64_t id2 = __ldcg(ids + off2);
+        if (id2 < 0) continue;
+        const double s2 = __ldcg(s64 + off2);
+        rank += (s2 > s) || (s2 == s && id2 < id);
+      }
     }
     if (rank < k) {
       out_s32[(size_t)q * k + rank] = (float)s;
@@ -972,55 +1013,54 @@ __device__ __forceinline__ void merge_shards_body(const double* __restrict__ s64
     }
   }
   // slots beyond the number of valid candidates
-  int valid = 0;
-  for (int c = lane; c < total; c += 32) {
-    const int sh = c / k, j = c - sh * k;
-    valid += ids[(size_t)sh * shard_stride + (size_t)q * k + j] >= 0;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-  for (int r = valid + lane; r < k; r += 32) {
+  for (int r = sh_valid + tid; r < k; r += kShardMergeThreads) {
     out_s32[(size_t)q * k + r] = -INFINITY;
     out_ids[(size_t)q * k + r] = -1;
   }
 }
 
-__global__ void merge_shards_kernel(const double* __restrict__ s64, const int64_t* __restrict__ ids,
-                                    int n_shards, int nq, int k, size_t shard_stride,
-                                    float* __restrict__ out_s32, int64_t* __restrict__ out_ids,
-                                    const uint32_t* __restrict__ poison) {
+__global__ void __launch_bounds__(kShardMergeThreads)
+merge_shards_kernel(const double* __restrict__ s64, const int64_t* __restrict__ ids, int n_shards, int nq, int k,
+                    size_t shard_stride, float* __restrict__ out_s32, int64_t* __restrict__ out_ids,
+                    const uint32_t* __restrict__ poison) {
   merge_shards_body(s64, ids, n_shards, k, shard_stride, out_s32, out_ids, poison && __ldcg(poison) != 0u);
 }
 
-// The exchange's wait + cross-shard merge in ONE launch (csrc/exchange.cu): every CTA (one warp = one query) first
+// The exchange's wait + cross-shard merge in ONE launch (csrc/exchange.cu): in every CTA (one per query) the first warp
 // waits until all `world` ranks have published sequence number `seq` in this rank's flag words (lane r polls rank
-// r's flag, ld.acquire.sys), then merges.  The wait is bounded by wall-clock time; on time-out the exchange is poisoned
-// (sticky), the sequence number is reported to the host through `status` (pinned, host-mapped) and the query comes
-// back empty — nothing traps, the shard stays resident.
-__global__ void wait_merge_shards_kernel(const uint32_t* __restrict__ flags, int world, uint32_t seq,
-                                         unsigned long long timeout_ns, uint32_t* poison, uint32_t* status,
-                                         const double* __restrict__ s64, const int64_t* __restrict__ ids, int nq, int k,
-                                         size_t shard_stride, float* __restrict__ out_s32, int64_t* __restrict__ out_ids) {
-  bool bad = *reinterpret_cast<volatile uint32_t*>(poison) != 0u;
-  if (!bad) {
-    const unsigned long long t0 = globaltimer_ns();
-    for (int r = threadIdx.x; r < world; r += 32) {
-      for (;;) {
-        uint32_t v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-        if ((int32_t)(v - seq) >= 0) break;
-        __nanosleep(200);
-        if (globaltimer_ns() - t0 > timeout_ns || *reinterpret_cast<volatile uint32_t*>(poison) != 0u) {
-          *reinterpret_cast<volatile uint32_t*>(poison) = 1u;
-          *reinterpret_cast<volatile uint32_t*>(status) = seq;
-          __threadfence_system();
-          bad = true;
-          break;
+// r's flag, ld.acquire.sys), then the CTA merges.  The wait is bounded by wall-clock time; on time-out the exchange is
+// poisoned (sticky), the sequence number is reported to the host through `status` (pinned, host-mapped) and the query
+// comes back empty — nothing traps, the CUDA context and the resident shard survive.
+__global__ void __launch_bounds__(kShardMergeThreads)
+wait_merge_shards_kernel(const uint32_t* __restrict__ flags, int world, uint32_t seq, unsigned long long timeout_ns,
+                         uint32_t* poison, uint32_t* status, const double* __restrict__ s64,
+                         const int64_t* __restrict__ ids, int nq, int k, size_t shard_stride,
+                         float* __restrict__ out_s32, int64_t* __restrict__ out_ids) {
+  bool bad = false;
+  if (threadIdx.x < 32) {
+    bad = *reinterpret_cast<volatile uint32_t*>(poison) != 0u;
+    if (!bad) {
+      const unsigned long long t0 = globaltimer_ns();
+      for (int r = threadIdx.x; r < world; r += 32) {
+        for (;;) {
+          uint32_t v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+          if ((int32_t)(v - seq) >= 0) break;
+          __nanosleep(200);
+          if (globaltimer_ns() - t0 > timeout_ns || *reinterpret_cast<volatile uint32_t*>(poison) != 0u) {
+            *reinterpret_cast<volatile uint32_t*>(poison) = 1u;
+            *reinterpret_cast<volatile uint32_t*>(status) = seq;
+            __threadfence_system();
+            bad = true;
+            break;
+          }
         }
       }
     }
-    bad = __any_sync(0xffffffffu, bad);
   }
+  // (bar.sync orders the other warps' loads behind the acquiring loads of warp 0 at CTA scope; the data words were
+  // released at system scope by the pushing rank before its flag)
+  bad = __syncthreads_or(bad) != 0;
   merge_shards_body(s64, ids, world, k, shard_stride, out_s32, out_ids, bad);
 }
 
@@ -1303,14 +1343,14 @@ cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st) {
 cudaError_t launch_merge_shards(const double* s64, const int64_t* ids, int n_shards, int nq, int k,
                                 size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st,
                                 const uint32_t* poison) {
-  merge_shards_kernel<<<nq, 32, 0, st>>>(s64, ids, n_shards, nq, k, shard_stride, out_s32, out_ids, poison);
+  merge_shards_kernel<<<nq, kShardMergeThreads, 0, st>>>(s64, ids, n_shards, nq, k, shard_stride, out_s32, out_ids, poison);
   return cudaGetLastError();
 }
 
 cudaError_t launch_wait_merge_shards(const uint32_t* flags, int world, uint32_t seq, unsigned long long timeout_ns,
                                      uint32_t* poison, uint32_t* status, const double* s64, const int64_t* ids, int nq, int k,
                                      size_t shard_stride, float* out_s32, int64_t* out_ids, cudaStream_t st) {
-  wait_merge_shards_kernel<<<nq, 32, 0, st>>>(flags, world, seq, timeout_ns, poison, status, s64, ids, nq, k, shard_stride,
+  wait_merge_shards_kernel<<<nq, kShardMergeThreads, 0, st>>>(flags, world, seq, timeout_ns, poison, status, s64, ids, nq, k, shard_stride,
                                               out_s32, out_ids);
   return cudaGetLastError();
 }

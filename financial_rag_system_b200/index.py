@@ -322,6 +322,14 @@ class VectorIndex:
         d["n"] = int(d["n"])
         return d
 
+    def read_profile_bracket_rel(self, ev_before, ev_after) -> tuple[float, float]:
+        """Bracket mode (3): (ms from `ev_before` to the first scan kernel's start, ms from the last scan kernel's end to
+        `ev_after`) for two recorded torch.cuda.Event objects — fill and drain of a pipelined run.  Call before
+        read_profile_ex (which resets the bracket)."""
+        buf = (C.c_double * 2)()
+        check(self._lib.frs_index_read_profile_bracket_rel(self._h, C.c_void_p(ev_before.cuda_event), C.c_void_p(ev_after.cuda_event), buf))
+        return float(buf[0]), float(buf[1])
+
     def read_profile_raw(self, max_searches: int = 256) -> np.ndarray:
         """[n, 7] ms: prep start / end, scan start / end, merge start / end, exchange end of the recorded searches
         (oldest first), relative to the first one's prep start.  Call before read_profile[_ex] (which resets)."""

@@ -282,6 +282,10 @@ int frs_index_read_profile(frs_index* idx, double* host_out4);
 /* {searches, prep ms, scan ms, merge ms, exchange ms (cross-shard wait + merge), scan-stream gap ms (end of one
  * scan kernel to the start of the next, summed), span ms (first prep start to last search end), 0} */
 int frs_index_read_profile_ex(frs_index* idx, double* host_out8);
+/* bracket mode (3) relative to the caller's events (cudaEvent_t handles recorded on this device): out2 = {ms from ev_before
+ * to the first scan kernel's start, ms from the last scan kernel's end to ev_after} = fill and drain of a pipelined run;
+ * call before frs_index_read_profile_ex (which resets the bracket) */
+int frs_index_read_profile_bracket_rel(frs_index* idx, void* ev_before, void* ev_after, double* host_out2);
 /* raw time line (diagnostics): per recorded search, oldest first, 7 event times in ms relative to the first search's first
  * event {prep start, prep end, scan start, scan end, merge start, merge end, exchange end}; returns the number of searches
  * written (<= max_searches), does not reset the recording */

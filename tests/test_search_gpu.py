@@ -265,6 +265,28 @@ def test_two_shards_on_one_gpu_equal_one_index():
         ix.close()
 
 
+@pytest.mark.parametrize("n_shards,nq,k", [(2, 32, 15), (8, 32, 15), (3, 5, 1), (16, 32, 32), (40, 7, 32)])
+def test_cross_shard_merge_equals_the_oracle(n_shards, nq, k):
+    """frs_merge_shards (one CTA per query, candidates staged in shared memory; 40 x 32 > 1024 candidates takes the
+    path that ranks from global memory) == so.merge_shards: order by (score desc, id asc), duplicated scores across
+    shards, empty slots (-1) anywhere, queries with fewer than k valid candidates."""
+    from financial_rag_system_b200.index import merge_shards
+
+    rng = np.random.default_rng(100 * n_shards + k)
+    sc = np.round(rng.standard_normal((n_shards, nq, k)), 1)          # many equal scores: ties break by id
+    ids = rng.permutation(n_shards * nq * k).reshape(n_shards, nq, k).astype(np.int64)
+    ids[rng.random(ids.shape) < 0.2] = -1
+    ids[:, 0, :] = -1                                                 # a query with no match anywhere
+    if nq > 1:
+        ids[:, 1, :] = -1
+        ids[0, 1, 0] = 7                                              # ... and one with a single match
+    sc[ids < 0] = -np.inf
+    mi, ms = merge_shards(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda(), k)
+    wi, ws = so.merge_shards(list(ids), list(sc), k)
+    assert np.array_equal(mi.cpu().numpy(), wi)
+    assert np.array_equal(ms.cpu().numpy(), ws.astype(np.float32))
+
+
 def test_peer_memory_exchange_equals_one_index():
     """The exchange step over peer memory (frs_exchange_*): three shards of ONE process linked by pointer, each
     pushes its block into every shard's gather buffer; every shard's merge equals the single-index search.
