@@ -671,7 +671,7 @@ def run_ours(args):
         if cx.world == 1 or os.environ.get("FRS_BENCH_ENCODERS_ALL_N"):
             import bench_encoders
 
-            for w in ("embed", "rerank", "pipeline"):
+            for w in ("embed", "embed_varlen", "rerank", "pipeline"):
                 try:
                     secondary[w] = bench_encoders.measure_compact(cx, w, ClockSampler, summarize_clocks)
                 except Exception as e:  # noqa: BLE001 - a secondary measurement must not cost the headline line
@@ -770,7 +770,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["search", "search_segmented", "embed", "rerank", "pipeline"], default="search",
+    ap.add_argument("--workload", choices=["search", "search_segmented", "embed", "embed_varlen", "rerank", "pipeline"], default="search",
                     help="search = the headline metric (default); the others are BASELINE.json configs[2] / configs[4], see bench_encoders.py")
     ap.add_argument("--queries", choices=list(bd.QUERY_KINDS), default="self", help="query set of the headline measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configs (quick runs, ncu captures)")

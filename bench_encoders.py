@@ -29,6 +29,7 @@ CHUNKS_PER_STEP = 148     # x 512 tokens = 75776 packed tokens per pass and per 
 SEQ = 512
 NQ, LIMIT, TOP_K = 32, 15, 5
 PIPE_ROWS = int(os.environ.get("FRS_PIPE_ROWS", 100_000))
+VARLEN_CHUNKS = 320  # ~73.6k tokens per step at a mean of 230: the same pass size as 148 x 512
 
 
 def flops(layers, lens):
@@ -46,12 +47,13 @@ def peaks():
 
 def metric_name(workload):
     return {"embed": "bge-small ingest embedding throughput (chunks x 512 tokens)",
+            "embed_varlen": "bge-small ingest embedding throughput (chunks of ~230 tokens, ragged)",
             "rerank": "MiniLM-L-6 cross-encoder rerank throughput (query, chunk) pairs",
             "pipeline": "retrieve+rerank: 32-query dynamic batch, top-15 each reranked to top-5"}[workload]
 
 
 def unit_name(workload):
-    return {"embed": "chunks/s", "rerank": "pairs/s", "pipeline": "queries/s"}[workload]
+    return {"embed": "chunks/s", "embed_varlen": "chunks/s", "rerank": "pairs/s", "pipeline": "queries/s"}[workload]
 
 
 def config(workload, world):
@@ -60,6 +62,12 @@ def config(workload, world):
                             f"tokens per step and per GPU (one per SM), CLS pooling + L2 normalise", "chunks_per_step_per_gpu": CHUNKS_PER_STEP,
                 "seq_len": SEQ, "parallelism": f"{world} GPU(s), independent chunks, weights replicated, no collective",
                 "l2": "activations of one pass (~580 MB) exceed the 126 MB L2"}
+    if workload == "embed_varlen":
+        return {"workload": f"bge-small-en-v1.5 shape, {VARLEN_CHUNKS} chunks per step and per GPU with lengths ~ N(230, 40) clipped to "
+                            "[16, 512] (SURVEY 8d config 3's realistic run: ~1000-char chunks, ingest.py:25-26), packed without padding, "
+                            "CLS pooling + L2 normalise", "chunks_per_step_per_gpu": VARLEN_CHUNKS,
+                "parallelism": f"{world} GPU(s), independent chunks, weights replicated, no collective",
+                "l2": "activations of one pass (~570 MB) exceed the 126 MB L2"}
     if workload == "rerank":
         return {"workload": f"ms-marco-MiniLM-L-6-v2 shape (6 layers, 22.7M params, seeded synthetic weights), {NQ}x{LIMIT} = {NQ * LIMIT} "
                             "(query, ~1000-char chunk) pairs per step, raw logits", "pairs_per_step_per_gpu": NQ * LIMIT,
@@ -186,7 +194,7 @@ def run_reference(args):
         cb = cpu_pipeline_config1()   # the stated config: 10k chunks, 10 concurrent requests, embed -> search -> rerank
         value = cb["value"]
     else:
-        value, cb = cpu_encode_rate(w)
+        value, cb = cpu_encode_rate("embed" if w == "embed_varlen" else w)
     line = {"impl": "reference", "metric": metric_name(w), "value": value, "unit": unit_name(w), "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(w, args.gpus), "cpu_baseline": cb,
@@ -219,14 +227,18 @@ def measure(cx, w, steps, warmup, ClockSampler, summarize_clocks, with_cpu=True)
     args.steps, args.warmup = steps, warmup
 
     retr = None
-    if w == "embed":
+    if w in ("embed", "embed_varlen"):
         model = Embedder(device=local_rank, max_tokens=CHUNKS_PER_STEP * SEQ, tokenizer=tok)
         bert, layers = model.bert, 12
-        lens = [SEQ] * CHUNKS_PER_STEP
+        if w == "embed":
+            lens = [SEQ] * CHUNKS_PER_STEP
+        else:
+            lens = np.clip(np.rint(np.random.default_rng(230).normal(230.0, 40.0, VARLEN_CHUNKS)), 16, SEQ).astype(np.int64).tolist()
+            assert sum(lens) <= CHUNKS_PER_STEP * SEQ
         cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
         ids = torch.from_numpy(rng.integers(1000, 30522, size=int(cu[-1])).astype(np.int32)).to(dev)
         step = lambda: bert.embed_device(ids, cu)  # noqa: E731
-        units = CHUNKS_PER_STEP
+        units = len(lens)
         # host-side inputs of the e2e leg: real chunk texts (~300 tokens each, the corpus the ingest path sees)
         _, texts, _ = synth.make_chunks(2048, seed=7 + rank)
         e2e_units = len(texts)
@@ -364,7 +376,7 @@ def measure(cx, w, steps, warmup, ClockSampler, summarize_clocks, with_cpu=True)
                          "dominant_class": top, "step_flops": fl},
             "clocks": summarize_clocks(samples),
         }
-        if world == 1 and with_cpu:
+        if world == 1 and with_cpu and w != "embed_varlen":  # (the CPU leg is timed on 512-token chunks: see --workload embed)
             if w == "pipeline":
                 r_e, _ = cpu_encode_rate("embed", 6.0)
                 r_r, cb = cpu_encode_rate("rerank", 10.0)
@@ -394,8 +406,8 @@ def run_ours(args, ClockSampler, summarize_clocks, Ctx):
 
 def measure_compact(cx, w, ClockSampler, summarize_clocks, steps=None):
     """The same measurement, boiled down for the `secondary` object of the headline line."""
-    steps = steps or {"embed": 10, "rerank": 10, "pipeline": 10}[w]
-    line = measure(cx, w, steps, 3, ClockSampler, summarize_clocks, with_cpu=cx.world == 1)
+    steps = steps or 10
+    line = measure(cx, w, steps, 3, ClockSampler, summarize_clocks, with_cpu=cx.world == 1 and w != "embed_varlen")
     if line is None:
         return None
     out = {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": steps,
