@@ -733,7 +733,8 @@ def run_ours(args):
                          "(profiles/scan_traffic.json), not re-measured in this run" if traffic else None,
                          "kernel": "scan_kernel<bf16>", "kernel_ms": r["scan_ms"], "kernel_ms_source": r["scan_ms_source"],
                          "algorithmic_bytes_per_launch": r["alg_bytes"], "peak_source": peak_src,
-                         "whole_step_frac": r["alg_bytes"] / (ms / steps * 1e-3) / 1e9 / peak},
+                         "whole_step_frac": r["alg_bytes"] / (ms / steps * 1e-3) / 1e9 / peak,
+                         "frac_of_nominal_8tbs": r["achieved"] / 8000.0},
             "breakdown_ms": {k: round(v, 5) for k, v in r["breakdown"].items()},
             "host_enqueue_us_per_step": round(r["host_enqueue_us_per_step"], 1),
             "timed_region_ms_per_rank": [round(v, 4) for v in r["ms_per_rank"]],

@@ -63,6 +63,45 @@ def test_pipelined_search_equals_synchronous_search(dtype, reserve):
     ix.close()
 
 
+def test_profiling_modes_leave_results_alone_and_account_for_the_run():
+    """The three event-profiling modes (per-kernel events, bracket around the scan launches, bracket relative to the
+    caller's own events = fill and drain of a pipelined run) return the same results as an unprofiled run and numbers
+    that add up: fill + n x scan + drain <= the caller's region, every part positive."""
+    n = 200_000
+    x, codes, g = _data(n, 17)
+    ix = _index(n)
+    ix.add(x, codes)
+    q, qc, qm = x[:32] + 0.05 * torch.randn((32, 384), generator=g, device="cuda"), _i32(codes[:32].cpu().numpy()), _i32(np.full(32, TICKER, np.uint32))
+    wi, ws = ix.search(q, qc, qm, 15)
+    torch.cuda.synchronize()
+    # per-kernel events + the raw time line
+    ix.set_profiling(1)
+    pend = [ix.search_async(q, qc, qm, 15) for _ in range(6)]
+    ix.wait(-1)
+    torch.cuda.synchronize()
+    tl = ix.read_profile_raw(16)
+    assert tl.shape == (6, 7) and np.all(np.diff(tl, axis=1)[:, [0, 2, 4]] > 0)       # every kernel has a duration
+    assert np.all(tl[:, 2] >= tl[:, 1]) and np.all(tl[:, 4] >= tl[:, 3])               # prep -> scan -> merge
+    prof = ix.read_profile_ex()
+    assert prof["n"] == 6 and prof["scan_ms"] > 0 and prof["span_ms"] >= tl[-1, 5] - 1e-3
+    # bracket, relative to the caller's events
+    ix.set_profiling(3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pend += [ix.search_async(q, qc, qm, 15) for _ in range(6)]
+    ix.wait(-1)
+    e1.record()
+    torch.cuda.synchronize()
+    fill, drain = ix.read_profile_bracket_rel(e0, e1)
+    br = ix.read_profile_ex()
+    assert br["n"] == 6 and fill > 0 and drain > 0 and br["scan_ms"] > 0
+    assert fill + br["scan_ms"] + drain <= e0.elapsed_time(e1) * 1.001 + 1e-3
+    ix.set_profiling(0)
+    for p in pend:
+        assert torch.equal(p.ids, wi) and torch.equal(p.scores, ws)
+    ix.close()
+
+
 def test_host_submit_collect_keeps_batches_in_flight():
     n = 40_000
     x, codes, g = _data(n, 5)
