@@ -1090,21 +1090,21 @@ __device__ __forceinline__ float round_tf32(float x) {
 // its CTAs are HBM-bound from the first tiles on — while the longer prep kernel, squeezed onto the few SMs a running
 // scan leaves free, became the pipeline's bottleneck at 1.25M rows per GPU: measured, reverted.)
 constexpr int kQsStride = kDim + 1;  // +1: lanes read different queries at the same element
-constexpr size_t kPrepSmem = ((size_t)kNQ * kQsStride + (size_t)kSampleRows * kDim + 32 * 32) * sizeof(float);
+constexpr size_t kPrepSmem = ((size_t)kNQ * kQsStride + (size_t)kSampleRows * kDim + (size_t)kSampleRows * 2 * 32) * sizeof(float);
 template <bool F32>
 __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
     const float* __restrict__ q, const uint32_t* __restrict__ code, const uint32_t* __restrict__ mask, int nq,
     void* __restrict__ qop, float* __restrict__ qrec, uint32_t* __restrict__ qcode, uint32_t* __restrict__ qmask,
     unsigned long long* stats, float* __restrict__ gmax, float* __restrict__ gsample,
     const void* __restrict__ rows, const uint32_t* __restrict__ codes, uint32_t n, int k, float eps) {
-  static_assert(kSampleRows * 2 % 32 == 0, "scoring maps (row, half) pairs to the 32 warps");
+  static_assert(kSampleRows == 64 && kNQ == 32, "scoring maps 16 groups of 4 rows x 2 halves to the 32 warps");
   static_assert(kSampleBlocks == 64, "the final selection holds two group maxima per lane");
   static_assert(kSampleGroupRows == 16 && kSampleRows / kSampleGroupRows == 4, "a CTA scores 4 groups of 16 rows");
   constexpr int kGroups = kSampleRows / kSampleGroupRows;
   extern __shared__ __align__(16) float psm[];
   float* rs = psm;                              // [kSampleRows][kDim] sampled rows widened to fp32
   float* qs = rs + kSampleRows * kDim;          // [32][kQsStride] prepared queries
-  float* part = qs + kNQ * kQsStride;           // [32 warps][32 queries] partial dot products
+  float* part = qs + kNQ * kQsStride;           // [kSampleRows][2 halves][32 queries] partial dot products
   __shared__ uint32_t smax[kSampleRows / kSampleGroupRows][kNQ], s_code[kNQ], s_mask[kNQ], s_rcode[kSampleRows];
   __shared__ bool s_last;
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1194,34 +1194,39 @@ __global__ void __launch_bounds__(32 * kNQ) prep_queries_kernel(
   }
   __syncthreads();
 
-  // 3. score: (row, half of the 384 elements) pairs over the 32 warps, lane -> query
-#pragma unroll 1
-  for (int p0 = 0; p0 < kSampleRows * 2; p0 += 32) {
-    const int pr = p0 + slot;
-    const int j = pr >> 1, h = pr & 1;
-    const float4* r4 = reinterpret_cast<const float4*>(rs + j * kDim) + h * (kDim / 8);
+  // 3. score: warp -> (4 consecutive rows, one half of the 384 elements), lane -> query.  The phase is bound by
+  //    shared-memory wavefronts, so a lane's query elements are read once per FOUR rows (8 wavefronts per 16 FMA;
+  //    one (row, half) pair per warp pass took 5 per 4).  Summation order per (row, half) and the order of the final
+  //    add are those of the one-pair form: the thresholds are bit-identical.
+  {
+    const int h = slot & 1, j0 = (slot >> 1) * 4;
     const float* qv = qs + lane * kQsStride + h * (kDim / 2);
-    float acc = 0.f;
-#pragma unroll 8
+    const float4* r4 = reinterpret_cast<const float4*>(rs + j0 * kDim) + h * (kDim / 8);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int i = 0; i < kDim / 8; ++i) {
-      const float4 a = r4[i];  // same address in every lane: broadcast
-      acc = fmaf(a.x, qv[4 * i], acc);
-      acc = fmaf(a.y, qv[4 * i + 1], acc);
-      acc = fmaf(a.z, qv[4 * i + 2], acc);
-      acc = fmaf(a.w, qv[4 * i + 3], acc);
+      const float q0 = qv[4 * i], q1 = qv[4 * i + 1], q2 = qv[4 * i + 2], q3 = qv[4 * i + 3];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 a = r4[r * (kDim / 4) + i];  // same address in every lane: broadcast
+        acc[r] = fmaf(a.x, q0, acc[r]);
+        acc[r] = fmaf(a.y, q1, acc[r]);
+        acc[r] = fmaf(a.z, q2, acc[r]);
+        acc[r] = fmaf(a.w, q3, acc[r]);
+      }
     }
-    part[slot * 32 + lane] = acc;
-    __syncthreads();
-    if (threadIdx.x < 16 * 32) {
-      const int jj = (p0 >> 1) + (threadIdx.x >> 5);  // row; lane = query
-      const int w0 = 2 * (threadIdx.x >> 5);
-      const float sc = part[w0 * 32 + lane] + part[(w0 + 1) * 32 + lane];
-      const uint32_t rc = s_rcode[jj];
-      if (lane < nq && rc != 0xFFFFFFFFu && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u)
-        atomicMax(&smax[jj / kSampleGroupRows][lane], f32_ordered(sc));
-    }
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) part[((j0 + r) * 2 + h) * 32 + lane] = acc[r];
   }
+  __syncthreads();
+#pragma unroll
+  for (int jj = slot; jj < kSampleRows; jj += 32) {  // row jj, lane = query
+    const float sc = part[(jj * 2) * 32 + lane] + part[(jj * 2 + 1) * 32 + lane];
+    const uint32_t rc = s_rcode[jj];
+    if (lane < nq && rc != 0xFFFFFFFFu && ((rc ^ s_code[lane]) & s_mask[lane]) == 0u)
+      atomicMax(&smax[jj / kSampleGroupRows][lane], f32_ordered(sc));
+  }
+  __syncthreads();
   if (threadIdx.x < kGroups * kNQ)
     gsample[(blockIdx.x * kGroups + (threadIdx.x >> 5)) * kNQ + lane] = f32_from_ordered(smax[threadIdx.x >> 5][lane]);
 
