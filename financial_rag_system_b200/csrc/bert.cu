@@ -1361,12 +1361,13 @@ static bool pdl_enabled() {
 template <int BN, int EPI>
 static cudaError_t launch_gemm_t(int sm_count, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                                  const CUtensorMap& to2, const GemmParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static DeviceOnce once;  // (one table per template instance)
   const size_t smem = GemmCfg<BN, EPI == kEpiResLN>::kTotal + 1024;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = once_per_device(once, [&] {
+      return cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   if (p.N % BN != 0 || p.K % 64 != 0 || p.N > 1536) return cudaErrorInvalidValue;
   GemmParams pd = p;
@@ -1451,14 +1452,11 @@ static cudaError_t launch_attention_kernel(int grid, size_t smem, cudaStream_t s
 
 cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUtensorMap& tmap_k, const CUtensorMap& tmap_vt,
                              const AttnParams& p, cudaStream_t st) {
-  static bool configured[64] = {};
+  static DeviceOnce once;
   const size_t smem = attn_smem_bytes();
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  cudaError_t e = once_per_device(once, [&] {
+    cudaError_t r = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r != cudaSuccess) return r;
     if (getenv("FRS_DEBUG_OCC")) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attention_kernel, kAttnThreads, smem);
@@ -1471,8 +1469,9 @@ cudaError_t launch_attention(int sm_count, const CUtensorMap& tmap_qk, const CUt
               "CTA(s) per SM (%d role set(s) per CTA; %d with no dynamic smem, %d with 64 KB)\n", kKB, smem, fa.sharedSizeBytes, fa.numRegs, nb,
               kAttnGroups, nb0, nb1);
     }
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+    return cudaSuccess;
+  });
+  if (e != cudaSuccess) return e;
   const int items = p.nqb * kHeadPairs;
   if (items <= 0) return cudaSuccess;
   const int ctas = (items + kAttnGroups - 1) / kAttnGroups;  // a CTA's groups take consecutive items

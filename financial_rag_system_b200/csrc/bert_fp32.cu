@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "bert.cuh"
+#include "common.cuh"
 
 namespace frs {
 
@@ -347,13 +348,12 @@ cudaError_t launch_layernorm_f32(const float* x, int M, const float* gamma, cons
 
 cudaError_t launch_attention_f32(const float* qkv, const QBlock* qblk, int nqb, float* ctx, cudaStream_t st) {
   if (nqb <= 0) return cudaSuccess;
-  static bool configured = false;
+  static DeviceOnce once;
   const size_t smem = (size_t)2 * kMaxSeq * kHeadDim * sizeof(float);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = once_per_device(once, [&] {
+    return cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (e != cudaSuccess) return e;
   attention_f32_kernel<<<dim3(nqb, kHeads), 128, smem, st>>>(qkv, qblk, ctx);
   return cudaGetLastError();
 }

@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 namespace frs {
 
 // ---------------------------------------------------------------------------------------------
@@ -535,6 +537,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+
+// Function attributes (the opt-in dynamic shared memory limit) live in a device's context: a launcher configures its
+// kernel once per (call site, device).  `done` is the call site's static table; a second thread that races the first
+// configures the kernel twice, which is harmless.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+  std::atomic<unsigned char> done[kMaxDevices];
+};
+template <typename F>
+inline cudaError_t once_per_device(DeviceOnce& o, F&& configure) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && o.done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+  e = configure();
+  if (e == cudaSuccess && tracked) o.done[dev].store(1, std::memory_order_release);
+  return e;
 }
 
 }  // namespace frs

@@ -1307,15 +1307,11 @@ template <bool F32, bool DUMP>
 static cudaError_t launch_scan_t(int grid, const CUtensorMap& tr, const CUtensorMap& tq,
                                  const ScanParams& p, cudaStream_t st) {
   const size_t smem = scan_smem_bytes(F32);
-  static bool configured[64] = {};  // per device: the attribute lives in the device's context
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
+  static DeviceOnce once;
+  cudaError_t e = once_per_device(once, [&] {
+    return cudaFuncSetAttribute(scan_kernel<F32, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(scan_kernel<F32, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
   scan_kernel<F32, DUMP><<<grid, kScanThreads, smem, st>>>(tr, tq, p);
   return cudaGetLastError();
 }
@@ -1329,17 +1325,13 @@ cudaError_t launch_scan(bool f32, bool dump, int grid, const CUtensorMap& tr, co
 cudaError_t launch_merge(bool f32, const MergeParams& p, cudaStream_t st) {
   const size_t smem = merge_smem_bytes(p.nparts);
   // the opt-in limit is set once per device to what the largest grid (kGmaxPad parts) needs
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  static DeviceOnce once;
+  cudaError_t e = once_per_device(once, [&] {
     const int lim = (int)merge_smem_bytes(kGmaxPad);
-    e = cudaFuncSetAttribute(merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+    cudaError_t r = cudaFuncSetAttribute(merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    return r != cudaSuccess ? r : cudaFuncSetAttribute(merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  });
+  if (e != cudaSuccess) return e;
   if (f32) merge_kernel<true><<<p.nq, kMergeThreads, smem, st>>>(p);
   else merge_kernel<false><<<p.nq, kMergeThreads, smem, st>>>(p);
   return cudaGetLastError();
@@ -1365,17 +1357,12 @@ cudaError_t launch_prep_queries(bool f32, const float* q, const uint32_t* code, 
                                 unsigned long long* stats, float* gmax, float* gsample, const void* rows,
                                 const uint32_t* codes, uint32_t n, int k, float eps, cudaStream_t st) {
   const size_t smem = kPrepSmem;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
+  static DeviceOnce once;
+  cudaError_t e = once_per_device(once, [&] {
+    cudaError_t r = cudaFuncSetAttribute(prep_queries_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return r != cudaSuccess ? r : cudaFuncSetAttribute(prep_queries_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(prep_queries_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(prep_queries_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
   if (f32)
     prep_queries_kernel<true><<<kSampleGrid, 32 * kNQ, smem, st>>>(q, code, mask, nq, qop, qrec, qcode, qmask, stats,
                                                                      gmax, gsample, rows, codes, n, k, eps);

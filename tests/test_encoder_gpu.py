@@ -329,6 +329,35 @@ def test_fp32_mode_meets_the_1e5_bound():
     ce32.close()
 
 
+def test_encoders_on_two_devices_of_one_process_agree(bge):
+    """One process, encoders on cuda:0 AND cuda:1 (a server process that embeds on every GPU of the box): the opt-in shared
+    memory limit of every kernel is a per-device attribute, so each launcher configures its kernel once per device.  The
+    second device's result must equal the first's bit for bit (same kernels, same inputs), in both precisions."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from financial_rag_system_b200.encoder import BertEncoder
+
+    enc0, w = bge
+    lens = [16, 230, 512, 1, 129, 77]
+    ids, tts, cu = _random_batch(lens, 41, pairs=True)
+    want = enc0.embed_packed(ids, cu, 0)
+    enc1 = BertEncoder(BGE_SMALL, w, device=1, max_tokens=2048)
+    got = enc1.embed_packed(ids, cu, 0)
+    assert np.array_equal(got, want)
+    enc1.close()
+    a = BertEncoder(BGE_SMALL, w, device=0, max_tokens=2048, precision="fp32")
+    b = BertEncoder(BGE_SMALL, w, device=1, max_tokens=2048, precision="fp32")
+    assert np.array_equal(a.embed_packed(ids, cu, 1), b.embed_packed(ids, cu, 1))
+    a.close()
+    b.close()
+    wc = synthetic_checkpoint(MINILM_L6_CE, 4321)
+    c0 = BertEncoder(MINILM_L6_CE, wc, device=0, max_tokens=2048)
+    c1 = BertEncoder(MINILM_L6_CE, wc, device=1, max_tokens=2048)
+    assert np.array_equal(c0.score_packed(ids, tts, cu), c1.score_packed(ids, tts, cu))
+    c0.close()
+    c1.close()
+
+
 def test_bf16_path_deviates_from_the_fp32_path_by_rounding_only(bge):
     """The two GPU paths share the structure; their difference is the bf16 rounding noise."""
     from financial_rag_system_b200.encoder import BertEncoder
