@@ -3,7 +3,7 @@
 QPS of exact top-15 cosine search over 10M x 384-d bf16 chunks, 32-query batches, on 1/2/4/8 B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload search|search_segmented|embed|rerank|pipeline] [--queries self|any|unrelated|one_ticker|rare]
+                  [--workload search|search_segmented|embed|embed_varlen|rerank|pipeline] [--queries self|any|unrelated|one_ticker|rare]
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one 32-query batch searched over the whole corpus (10M rows in total, sharded over the
@@ -18,6 +18,8 @@ N ranks: strong scaling, as BASELINE.json quotes the metric).  One JSON line is 
   roofline   scan kernel only: algorithmic bytes (rows*768 + rows*4 per launch) / CUDA-event time of the scan
              kernel measured live by library-side events on the stream it is launched on
   breakdown  per-step kernel milliseconds {prep, scan, merge, exchange, gap} from the same events
+  per_rank   every rank's scan-kernel time and the fill (start -> first scan kernel) and drain (last scan kernel's
+             end -> end) of its timed region: what a short pipelined run pays besides its scans
   parity_checked
              how many of the 32 queries of the timed batch were verified, ids and scores, against an independent
              path (every row's tensor-core score dumped, torch.topk, fp64 rescoring of the candidates, cross-rank
